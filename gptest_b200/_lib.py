@@ -1,0 +1,255 @@
+"""ctypes binding of libgpb200.so (the C ABI declared in include/gpb200.h).
+
+There is no CPU fallback: if the shared library is missing it is an ImportError-like
+RuntimeError telling how to build it, and if no B200 is present ``Handle()`` raises with the
+library's own message.
+"""
+import ctypes as C
+import os
+import subprocess
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libgpb200.so')
+CSRC = os.path.join(_HERE, 'csrc')
+
+_lib = None
+_lock = threading.Lock()
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+c_lp = C.POINTER(C.c_int64)
+c_fp = C.POINTER(C.c_float)
+
+# name -> (restype, argtypes): exactly the declarations of include/gpb200.h
+SIGNATURES = {
+    'gpb_version': (C.c_int, []),
+    'gpb_create': (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    'gpb_set_stream': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'gpb_get_stream': (C.c_void_p, [C.c_void_p]),
+    'gpb_destroy': (C.c_int, [C.c_void_p]),
+    'gpb_last_error': (C.c_char_p, [C.c_void_p]),
+    'gpb_set_option': (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    'gpb_get_timings': (C.c_int, [C.c_void_p, c_fp, C.c_int]),
+    'gpb_launch_count': (C.c_int64, [C.c_void_p]),
+    'gpb_set_train': (C.c_int, [C.c_void_p, c_dp, C.c_int64, C.c_int32, c_dp]),
+    'gpb_set_train_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    'gpb_se_ard_kxx': (C.c_int, [C.c_void_p, c_dp, C.c_void_p, C.c_int32, C.c_int32]),
+    'gpb_se_ard_kxz': (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int64, C.c_void_p, C.c_int32]),
+    'gpb_sqdist': (C.c_int, [C.c_void_p, c_dp, C.c_int64, c_dp]),
+    'gpb_gpr_nlml': (C.c_int, [C.c_void_p, c_dp, C.c_double, c_dp, c_dp, c_ip]),
+    'gpb_gpr_predict': (C.c_int, [C.c_void_p, c_dp, C.c_double, c_dp, C.c_int64, c_dp, c_dp, c_ip]),
+    'gpb_gpr_nlml_batched': (C.c_int, [C.c_void_p, c_dp, C.c_int64, C.c_double, c_dp, c_dp, c_ip]),
+    'gpb_potrf_lower_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, c_ip]),
+    'gpb_potrf_lower': (C.c_int, [C.c_void_p, c_dp, C.c_int64, c_ip]),
+    'gpb_dgemm_nt_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                   C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_double]),
+    'gpb_gpc_laplace': (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int32, C.c_double, C.c_int32, C.c_int32, c_dp,
+                                  c_dp, c_ip, c_dp, c_dp, c_ip]),
+    'gpb_gpc_predict': (C.c_int, [C.c_void_p, c_dp, C.c_int64, c_dp, c_dp, c_dp]),
+    'gpb_pref_laplace': (C.c_int, [C.c_void_p, c_lp, c_dp, C.c_int64, c_dp, C.c_double, C.c_double, C.c_int32,
+                                   C.c_int32, C.c_int32, c_dp, c_dp, c_ip, c_dp, c_dp, c_ip]),
+    'gpb_pref_derivatives': (C.c_int, [C.c_void_p, c_lp, c_dp, C.c_int64, C.c_int64, c_dp, C.c_double,
+                                       C.c_int32, c_dp, c_dp]),
+    'gpb_microbench': (C.c_int, [C.c_void_p, C.c_int32, c_dp]),
+}
+
+
+def build(verbose=False):
+    """Compile libgpb200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(['make', '-j8', '-C', CSRC], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout[-4000:])
+        print(r.stderr[-4000:])
+    if r.returncode:
+        raise RuntimeError('building libgpb200.so failed')
+    return LIB_PATH
+
+
+def load():
+    """Load the shared library (once) and attach the prototypes."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                'libgpb200.so is not built (%s). Run `python -c "import __graft_entry__ as g; g.build()"` '
+                'or `make -C gptest_b200/csrc`. There is no CPU fallback.' % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError here = header and library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+class GpbError(RuntimeError):
+    pass
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def as_f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class Handle:
+    """One device + one stream + resident work space (a gpb_handle)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        hp = C.c_void_p()
+        rc = self.lib.gpb_create(int(device), C.byref(hp))
+        if rc != 0:
+            raise GpbError('gpb_create failed: %s' % self.lib.gpb_last_error(None).decode())
+        self.h = hp
+        self.device = device
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.gpb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            raise GpbError('libgpb200 error %d: %s' % (rc, self.lib.gpb_last_error(self.h).decode()))
+
+    # ---- plumbing --------------------------------------------------------------------------
+    def set_stream(self, stream_ptr):
+        self.check(self.lib.gpb_set_stream(self.h, C.c_void_p(stream_ptr)))
+
+    def stream(self):
+        return self.lib.gpb_get_stream(self.h) or 0
+
+    def set_option(self, name, value):
+        self.check(self.lib.gpb_set_option(self.h, name.encode(), int(value)))
+
+    def timings(self):
+        buf = (C.c_float * 8)()
+        self.lib.gpb_get_timings(self.h, buf, 8)
+        t = list(buf)
+        return dict(kbuild_ms=t[0], factor_ms=t[1], finish_ms=t[2], grad_ms=t[3], total_ms=t[4])
+
+    def launch_count(self):
+        return int(self.lib.gpb_launch_count(self.h))
+
+    # ---- data ------------------------------------------------------------------------------
+    def set_train(self, X, y=None):
+        X = as_f64(X)
+        X = X.reshape(len(X), -1)
+        yp = None
+        if y is not None:
+            y = as_f64(y).reshape(-1)
+            assert len(y) == len(X)
+            yp = _dp(y)
+        self.n, self.d = X.shape
+        self.check(self.lib.gpb_set_train(self.h, _dp(X), X.shape[0], X.shape[1], yp))
+
+    # ---- covariance --------------------------------------------------------------------------
+    def kxx(self, khyp, flags=0):
+        khyp = as_f64(khyp)
+        out = np.empty((self.n, self.n))
+        self.check(self.lib.gpb_se_ard_kxx(self.h, _dp(khyp), out.ctypes.data_as(C.c_void_p), 0, flags))
+        return out
+
+    def kxx_dev(self, khyp, dev_ptr, flags=0):
+        khyp = as_f64(khyp)
+        self.check(self.lib.gpb_se_ard_kxx(self.h, _dp(khyp), C.c_void_p(dev_ptr), 1, flags))
+
+    def kxz(self, khyp, Z):
+        khyp = as_f64(khyp)
+        Z = as_f64(Z)
+        Z = Z.reshape(len(Z), -1)
+        out = np.empty((self.n, Z.shape[0]))
+        self.check(self.lib.gpb_se_ard_kxz(self.h, _dp(khyp), _dp(Z), Z.shape[0], out.ctypes.data_as(C.c_void_p), 0))
+        return out
+
+    def sqdist(self, B):
+        B = as_f64(B)
+        B = B.reshape(len(B), -1)
+        out = np.empty((self.n, B.shape[0]))
+        self.check(self.lib.gpb_sqdist(self.h, _dp(B), B.shape[0], _dp(out)))
+        return out
+
+    # ---- regression ----------------------------------------------------------------------------
+    def gpr_nlml(self, khyp, mean=0.0, want_grad=False):
+        khyp = as_f64(khyp)
+        val = C.c_double()
+        info = C.c_int32()
+        grad = np.empty(len(khyp)) if want_grad else None
+        self.check(self.lib.gpb_gpr_nlml(self.h, _dp(khyp), float(mean), C.byref(val),
+                                         _dp(grad) if want_grad else None, C.byref(info)))
+        if info.value > 0:
+            raise np.linalg.LinAlgError('Matrix is not positive definite (leading minor %d)' % info.value)
+        return (val.value, grad) if want_grad else val.value
+
+    def gpr_predict(self, khyp, Z, mean=0.0):
+        khyp = as_f64(khyp)
+        Z = as_f64(Z)
+        Z = Z.reshape(len(Z), -1)
+        m = Z.shape[0]
+        fz, cov = np.empty(m), np.empty(m)
+        info = C.c_int32()
+        self.check(self.lib.gpb_gpr_predict(self.h, _dp(khyp), float(mean), _dp(Z), m, _dp(fz), _dp(cov), C.byref(info)))
+        if info.value > 0:
+            raise np.linalg.LinAlgError('Matrix is not positive definite (leading minor %d)' % info.value)
+        return fz, cov
+
+    def gpr_nlml_batched(self, khyp, mean=0.0, want_grad=False):
+        khyp = as_f64(khyp)
+        B, p = khyp.shape
+        val = np.empty(B)
+        info = np.zeros(B, dtype=np.int32)
+        grad = np.empty((B, p)) if want_grad else None
+        self.check(self.lib.gpb_gpr_nlml_batched(self.h, _dp(khyp), B, float(mean), _dp(val),
+                                                 _dp(grad) if want_grad else None, info.ctypes.data_as(c_ip)))
+        return (val, grad, info) if want_grad else (val, info)
+
+    # ---- dense hooks ------------------------------------------------------------------------
+    def potrf(self, A):
+        A = np.array(A, dtype=np.float64, order='C')
+        info = C.c_int32()
+        self.check(self.lib.gpb_potrf_lower(self.h, _dp(A), A.shape[0], C.byref(info)))
+        if info.value > 0:
+            raise np.linalg.LinAlgError('Matrix is not positive definite (leading minor %d)' % info.value)
+        return A
+
+    def potrf_dev(self, dev_ptr, n, lda):
+        info = C.c_int32()
+        self.check(self.lib.gpb_potrf_lower_dev(self.h, C.c_void_p(dev_ptr), n, lda, C.byref(info)))
+        return info.value
+
+    def dgemm_nt_dev(self, c_ptr, ldc, a_ptr, lda, b_ptr, ldb, M, N, K, alpha, beta):
+        self.check(self.lib.gpb_dgemm_nt_dev(self.h, C.c_void_p(c_ptr), ldc, C.c_void_p(a_ptr), lda,
+                                             C.c_void_p(b_ptr), ldb, M, N, K, alpha, beta))
+
+    def microbench(self, kind):
+        v = C.c_double()
+        self.check(self.lib.gpb_microbench(self.h, kind, C.byref(v)))
+        return v.value
+
+
+_default = {}
+
+
+def default_handle(device=0):
+    """Process-wide handle per device, shared by the drop-in classes (work space is reused)."""
+    h = _default.get(device)
+    if h is None:
+        h = _default[device] = Handle(device)
+    return h

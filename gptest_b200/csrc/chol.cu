@@ -1,0 +1,160 @@
+// chol.cu - host driver of the blocked right-looking Cholesky sweep.
+//
+// Replaces np.linalg.cholesky + the two np.linalg.solve calls of GPr.py:62-63 / GPpref.py:128-129.
+//
+// The matrix is cut into 128x128 tiles; an outer block column is nb_tiles tiles wide.
+//   panel(kb):   for each tile column k of the block
+//                   tile_potrf_inv(k,k)           L_kk and W_k = L_kk^-1           (1 CTA)
+//                   A[i,k] <- A[i,k] W_k^T        all rows below, DMMA product     (R-k-1 CTAs)
+//                   A[i,j] -= A[i,k] A[j,k]^T     remaining columns of the block   (K = 128)
+//   trail(kb):   A[i,j] -= sum_k A[i,k] A[j,k]^T  everything right of the block    (K = 128 nb)
+// Rows appended under the symmetric part are right-hand sides stored as rows: they receive the
+// same TRSM/update and end up multiplied by L^-T, i.e. the forward solves L^-1 y (and
+// L^-1 Kxz for the predictive variance) cost no extra pass.
+//
+// Look-ahead: the columns of the next panel are updated first, then the next panel is factored
+// on a high-priority side stream while the main stream updates the rest of the trailing matrix.
+// Both streams are ordered with events only - the host never blocks inside the sweep.
+#include "gpb_context.cuh"
+
+namespace gpb {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    GPB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) throw Error{"cuTensorMapEncodeTiled not available in this driver"};
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 3-D fp64 tensor map {cols, rows, batch}; box = {16 doubles (128 B), 128 rows, 1}; 128B swizzle;
+// out-of-bounds rows read as zero (partial last row tile of the appended rows).
+void make_tensor_map(CUtensorMap* map, const double* base, int64_t cols, int64_t rows, int64_t batch,
+                     int64_t row_pitch, int64_t batch_pitch) {
+  GPB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "matrix base must be 16-byte aligned");
+  GPB_REQUIRE(row_pitch % 2 == 0, "leading dimension must be even (16-byte row pitch)");
+  if (batch_pitch <= 0) batch_pitch = rows * row_pitch;
+  GPB_REQUIRE(batch_pitch % 2 == 0, "batch pitch must be even");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows),
+                        static_cast<cuuint64_t>(batch < 1 ? 1 : batch)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_pitch) * 8, static_cast<cuuint64_t>(batch_pitch) * 8};
+  cuuint32_t box[3] = {GEMM_KB, TILE, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides,
+                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error{"cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r))};
+}
+
+void finalize_factor_mat(FactorMat& m) {
+  GPB_REQUIRE(m.n_pad % TILE == 0, "n_pad must be a multiple of 128");
+  make_tensor_map(&m.mapA, m.A, m.ld, m.rows_total, m.batch, m.ld, m.batch_stride);
+  make_tensor_map(&m.mapD, m.Dinv, TILE, m.n_pad, m.batch, TILE, m.dinv_bs);
+}
+
+namespace {
+
+struct Sweep {
+  gpb_handle* h;
+  FactorMat& m;
+  bool factor;
+  int nt, R;
+
+  GemmArgs base() const {
+    GemmArgs a{};
+    a.C = m.A;
+    a.ldc = m.ld;
+    a.c_batch_stride = m.batch_stride;
+    a.rows_total = static_cast<int>(m.rows_total);
+    a.R = R;
+    if (factor) {
+      a.tri = 1;
+    } else {
+      a.tri = 0;
+      a.i0 = nt;
+    }
+    return a;
+  }
+  // A[i,k] <- A[i,k] * W_k^T for the rows below tile (k,k) (and the appended rows)
+  void trsm(int k, cudaStream_t st) {
+    GemmArgs a = base();
+    a.j0 = k; a.j1 = k + 1; a.i_off = 1;
+    a.ka0 = k * TILE; a.kb0 = 0; a.nk = TILE / GEMM_KB; a.b_row0 = 0;
+    a.epi = 0;
+    if (gemm_region_tiles(a) <= 0) return;
+    launch_dmma_gemm(m.mapA, m.mapD, a, m.batch, st);
+    ++h->launches;
+  }
+  // A[i,j] -= sum_{k in [ka,kb)} A[i,k] A[j,k]^T for tile columns j in [c0,c1), rows i >= j
+  void update(int c0, int c1, int ka, int kb, cudaStream_t st) {
+    if (c1 <= c0 || kb <= ka) return;
+    GemmArgs a = base();
+    a.j0 = c0; a.j1 = c1; a.i_off = 0;
+    a.ka0 = ka * TILE; a.kb0 = ka * TILE; a.nk = (kb - ka) * TILE / GEMM_KB; a.b_row0 = 0;
+    a.epi = 1;
+    if (gemm_region_tiles(a) <= 0) return;
+    launch_dmma_gemm(m.mapA, m.mapA, a, m.batch, st);
+    ++h->launches;
+  }
+  void panel(int kb, int kend, cudaStream_t st) {
+    for (int k = kb; k < kend; ++k) {
+      if (factor) {
+        TilePotrfArgs t{};
+        t.A = m.A; t.lda = m.ld; t.a_batch_stride = m.batch_stride; t.k = k;
+        t.Dinv = m.Dinv; t.d_batch_stride = m.dinv_bs;
+        t.diag = m.diag; t.diag_batch_stride = m.diag_bs; t.info = m.info;
+        launch_tile_potrf_inv(t, m.batch, st);
+        ++h->launches;
+      }
+      trsm(k, st);
+      update(k + 1, kend, k, k + 1, st);
+    }
+  }
+};
+
+}  // namespace
+
+void chol_sweep(gpb_handle* h, FactorMat& m, bool factor) {
+  const int nt = static_cast<int>(m.n_pad / TILE);
+  const int R = static_cast<int>((m.rows_total + TILE - 1) / TILE);
+  Sweep s{h, m, factor, nt, R};
+  const int nb = h->nb_tiles < 1 ? 1 : h->nb_tiles;
+  // without a symmetric part to factor there is no panel critical path: plain order
+  const bool la = h->lookahead && factor && m.batch == 1 && nt > nb;
+
+  if (!la) {
+    for (int kb = 0; kb < nt; kb += nb) {
+      const int kend = kb + nb < nt ? kb + nb : nt;
+      s.panel(kb, kend, h->s0);
+      s.update(kend, nt, kb, kend, h->s0);
+    }
+    return;
+  }
+
+  s.panel(0, nb < nt ? nb : nt, h->s0);
+  for (int kb = 0; kb < nt; kb += nb) {
+    const int kend = kb + nb < nt ? kb + nb : nt;
+    if (kend >= nt) break;
+    const int nend = kend + nb < nt ? kend + nb : nt;
+    s.update(kend, nend, kb, kend, h->s0);            // columns of the next panel first
+    cudaEvent_t eu = h->next_event();
+    GPB_CUDA(cudaEventRecord(eu, h->s0));
+    GPB_CUDA(cudaStreamWaitEvent(h->s1, eu, 0));
+    s.panel(kend, nend, h->s1);                        // next panel on the side stream ...
+    cudaEvent_t ep = h->next_event();
+    GPB_CUDA(cudaEventRecord(ep, h->s1));
+    s.update(nend, nt, kb, kend, h->s0);               // ... while the rest of the update runs
+    GPB_CUDA(cudaStreamWaitEvent(h->s0, ep, 0));
+  }
+}
+
+}  // namespace gpb

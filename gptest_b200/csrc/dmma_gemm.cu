@@ -1,0 +1,248 @@
+// dmma_gemm.cu - the kernel the factorisation spends its time in.
+//
+// C(it,jt) (op)= sum_k A(it,k) * B(jt,k)^T on 128x128 tiles of row-major fp64 matrices, used for
+//   - the trailing SYRK/GEMM update of the blocked Cholesky (np.linalg.cholesky, GPr.py:62),
+//   - the panel TRSM written as a product with the inverted diagonal tile,
+//   - the fused forward solves (rows appended under K), TRTRI/LAUUM of the gradient stage.
+//
+// B200 mapping
+//   * tcgen05 has no f64 kind: the FP64 tensor path on sm_100a is the warp-level
+//     mma.sync.m8n8k4 (SASS DMMA.8x8x4), operands in registers.
+//   * operand slabs (128 rows x 16 doubles = 128-byte rows) are brought in by TMA
+//     (cp.async.bulk.tensor, SASS UTMALDG) with the 128B swizzle through a 4-stage
+//     full/empty mbarrier ring; one producer warp, eight DMMA consumer warps (2 x 4, each
+//     64 x 32 of the tile = 32 DMMA accumulators).
+//   * fragment rows are taken with a stride of two tile rows ("parity" fragments): under the
+//     128B swizzle the 16 lanes of a half warp then read 8 distinct 16-byte chunks over 4 rows
+//     = all 32 banks once, so every 64-bit fragment load is conflict free.
+//   * per 16-wide slab a warp issues 128 DMMA for 48 LDS.64: the FP64 tensor pipe is the only
+//     busy unit; shared-memory and issue bandwidth stay below 20 %.
+#include "gpb_kernels.cuh"
+
+namespace gpb {
+
+__device__ __forceinline__ void decode_tile(const GemmArgs& p, int idx, int& it, int& jt) {
+  if (p.tri) {
+    // column c (jt = j0 + c) holds H - c tiles, H = R - j0 - i_off; off(c) = c*H - c(c-1)/2
+    const int H = p.R - p.j0 - p.i_off;
+    const double b = 2.0 * H + 1.0;
+    int c = static_cast<int>((b - sqrt(b * b - 8.0 * idx)) * 0.5);
+    if (c < 0) c = 0;
+    while ((c + 1) * H - (c + 1) * c / 2 <= idx) ++c;
+    while (c * H - c * (c - 1) / 2 > idx) --c;
+    jt = p.j0 + c;
+    it = jt + p.i_off + (idx - (c * H - c * (c - 1) / 2));
+  } else {
+    const int nrows = p.R - p.i0;
+    jt = p.j0 + idx / nrows;
+    it = p.i0 + idx % nrows;
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                    const GemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
+  uint64_t* empty = full + GEMM_STAGES;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int batch = blockIdx.y;
+  int it, jt;
+  decode_tile(p, blockIdx.x, it, jt);
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < GEMM_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], GEMM_CONSUMER_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == GEMM_CONSUMER_WARPS) {
+    // ---------------- TMA producer: one elected lane ----------------
+    if (lane == 0) {
+      tma_prefetch_desc(&mapA);
+      tma_prefetch_desc(&mapB);
+      const int arow = it * TILE;
+      const int brow = p.b_row0 + jt * TILE;
+      for (int s = 0; s < p.nk; ++s) {
+        const int st = s % GEMM_STAGES;
+        if (s >= GEMM_STAGES) mbar_wait(&empty[st], ((s / GEMM_STAGES) - 1) & 1);
+        uint8_t* dst = smem + st * GEMM_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[st], GEMM_STAGE_BYTES);
+        tma_load_3d(dst, &mapA, &full[st], p.ka0 + GEMM_KB * s, arow, batch);
+        tma_load_3d(dst + TILE * GEMM_KB * 8, &mapB, &full[st], p.kb0 + GEMM_KB * s, brow, batch);
+      }
+    }
+    return;
+  }
+
+  // ---------------- DMMA consumers ----------------
+  const int wm = warp >> 2;        // 0..1 : 64-row half of the tile
+  const int wn = warp & 3;         // 0..3 : 32-column quarter of the tile
+  const int g = lane >> 2;         // fragment row (A) / column (B)
+  const int t = lane & 3;          // fragment k index
+  const int th = t >> 1;
+
+  double* Cb = p.C + static_cast<int64_t>(batch) * p.c_batch_stride;
+  const int64_t row_base = static_cast<int64_t>(it) * TILE + wm * 64;
+  const int64_t col_base = static_cast<int64_t>(jt) * TILE + wn * 32;
+  if (p.epi == 1) {
+    // pull this warp's 64 x 32 piece of C towards L2 while the k loop runs
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = lane + 32 * q;
+      const int64_t row = row_base + (idx >> 1);
+      if (row < p.rows_total) prefetch_l2(Cb + row * p.ldc + col_base + (idx & 1) * 16);
+    }
+  }
+
+  // byte offsets inside a slab (row r, column c): r*128 + (((c>>1) ^ (r&7)) << 4) + (c&1)*8
+  uint32_t a_off[2], b_off[2], xr[2];
+#pragma unroll
+  for (int par = 0; par < 2; ++par) {
+    xr[par] = ((g & 3) << 1) | par;
+    a_off[par] = (wm * 64 + 2 * g + par) * 128 + (t & 1) * 8;
+    b_off[par] = (wn * 32 + 2 * g + par) * 128 + (t & 1) * 8;
+  }
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int s = 0; s < p.nk; ++s) {
+    const int st = s % GEMM_STAGES;
+    mbar_wait(&full[st], (s / GEMM_STAGES) & 1);
+    const uint8_t* sa = smem + st * GEMM_STAGE_BYTES;
+    const uint8_t* sb = sa + TILE * GEMM_KB * 8;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int par = 0; par < 2; ++par) {
+        const uint32_t chunk = ((2 * kk + th) ^ xr[par]) << 4;
+#pragma unroll
+        for (int grp = 0; grp < 4; ++grp)
+          af[grp * 2 + par] = *reinterpret_cast<const double*>(sa + a_off[par] + grp * 2048 + chunk);
+#pragma unroll
+        for (int grp = 0; grp < 2; ++grp)
+          bf[grp * 2 + par] = *reinterpret_cast<const double*>(sb + b_off[par] + grp * 2048 + chunk);
+      }
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int nj = 0; nj < 4; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], af[mi], bf[nj]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+  }
+
+  // ---------------- epilogue: each lane owns 4 consecutive columns per (row, column group) -------
+  // fragment (grp_m, par_m) row g  -> tile row 16 grp_m + 2 g + par_m
+  // fragment (grp_n, par_n) col 2t+e -> tile col 16 grp_n + 4 t + 2 e + par_n
+#pragma unroll
+  for (int gm = 0; gm < 4; ++gm) {
+#pragma unroll
+    for (int pm = 0; pm < 2; ++pm) {
+      const int64_t row = row_base + 16 * gm + 2 * g + pm;
+      if (row < p.rows_total) {
+        const int mi = gm * 2 + pm;
+#pragma unroll
+        for (int gn = 0; gn < 2; ++gn) {
+          double* ptr = Cb + row * p.ldc + col_base + 16 * gn + 4 * t;
+          double2 lo = make_double2(acc[mi][gn * 2][0], acc[mi][gn * 2 + 1][0]);
+          double2 hi = make_double2(acc[mi][gn * 2][1], acc[mi][gn * 2 + 1][1]);
+          if (p.epi == 1) {
+            const double2 c0 = *reinterpret_cast<const double2*>(ptr);
+            const double2 c1 = *reinterpret_cast<const double2*>(ptr + 2);
+            lo.x = c0.x - lo.x; lo.y = c0.y - lo.y;
+            hi.x = c1.x - hi.x; hi.y = c1.y - hi.y;
+          }
+          *reinterpret_cast<double2*>(ptr) = lo;
+          *reinterpret_cast<double2*>(ptr + 2) = hi;
+        }
+      }
+    }
+  }
+}
+
+int gemm_region_tiles(const GemmArgs& a) {
+  const int ncols = a.j1 - a.j0;
+  if (ncols <= 0) return 0;
+  if (a.tri) {
+    const int H = a.R - a.j0 - a.i_off;
+    if (H - (ncols - 1) <= 0) return -1;
+    return ncols * H - ncols * (ncols - 1) / 2;
+  }
+  if (a.R - a.i0 <= 0) return 0;
+  return ncols * (a.R - a.i0);
+}
+
+void dmma_gemm_init() {
+  GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GEMM_SMEM_BYTES));
+}
+
+void launch_dmma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmArgs a, int batch,
+                      cudaStream_t st) {
+  const int ntiles = gemm_region_tiles(a);
+  GPB_REQUIRE(ntiles >= 0, "dmma_gemm: empty column in trapezoid region");
+  if (ntiles == 0 || a.nk == 0) return;
+  a.ntiles = ntiles;
+  dim3 grid(ntiles, batch, 1);
+  dmma_gemm_nt_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(mapA, mapB, a);
+  GPB_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------
+// Pipe-rate micro-benchmarks: fix the FP64 roofline denominator on the box itself.
+// ---------------------------------------------------------------------------------------
+constexpr int MB_ITERS = 4096;
+__global__ void __launch_bounds__(256) mb_dmma_kernel(double* sink) {
+  double c[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < MB_ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dmma884(c[i][0], c[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+  if (s == 123.456) sink[0] = s;
+}
+__global__ void __launch_bounds__(256) mb_dfma_kernel(double* sink) {
+  double c[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c[i] = i;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
+  for (int it = 0; it < MB_ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i];
+  if (s == 123.456) sink[0] = s;
+}
+double launch_microbench(int kind, double* sink, cudaStream_t st) {
+  const int blocks = 148 * 8, threads = 256;
+  if (kind == 0) {
+    mb_dmma_kernel<<<blocks, threads, 0, st>>>(sink);
+    GPB_CUDA(cudaGetLastError());
+    return 2.0 * 256.0 * 16.0 * MB_ITERS * (threads / 32) * static_cast<double>(blocks);
+  }
+  mb_dfma_kernel<<<blocks, threads, 0, st>>>(sink);
+  GPB_CUDA(cudaGetLastError());
+  return 2.0 * 16.0 * MB_ITERS * threads * static_cast<double>(blocks);
+}
+
+}  // namespace gpb

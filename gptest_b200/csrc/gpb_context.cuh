@@ -1,0 +1,99 @@
+// gpb_context.cuh - the handle behind the C ABI: device buffers, streams, tensor maps.
+#pragma once
+#include <vector>
+
+#include "gpb_kernels.cuh"
+
+namespace gpb {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  void ensure(size_t want) {
+    if (want <= bytes) return;
+    release();
+    GPB_CUDA(cudaMalloc(&p, want));
+    bytes = want;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+  ~DevBuf() { release(); }
+};
+
+// A matrix being factored / swept: n_pad x n_pad symmetric part (lower triangle used) followed by
+// extra rows (right-hand sides stored as rows, solved "for free" by the sweep).
+struct FactorMat {
+  double* A = nullptr;
+  int64_t ld = 0;            // elements, = columns of the tensor map
+  int64_t n_pad = 0;         // multiple of 128
+  int64_t rows_total = 0;    // n_pad + number of extra rows
+  int batch = 1;
+  int64_t batch_stride = 0;  // elements
+  double* Dinv = nullptr;    // per batch nt*128 x 128
+  int64_t dinv_bs = 0;
+  double* diag = nullptr;    // per batch n_pad
+  int64_t diag_bs = 0;
+  int* info = nullptr;       // per batch
+  CUtensorMap mapA, mapD;
+};
+
+}  // namespace gpb
+
+struct gpb_handle {
+  int device = 0;
+  cudaStream_t s0 = nullptr;     // the handle's stream (all results are ordered on it)
+  bool own_s0 = false;
+  cudaStream_t s1 = nullptr;     // high-priority side stream for the look-ahead panel
+  std::string err;
+  int64_t launches = 0;
+
+  // options
+  int lookahead = 1;
+  int nb_tiles = 2;
+  int64_t batch_chunk = 0;       // 0 = auto
+
+  // training data (GPr.py:25-26 keeps trainInput / trainTarget on the object)
+  int64_t n = 0, n_pad = 0;
+  int d = 0;
+  bool has_y = false;
+  gpb::DevBuf X, y, yc;
+
+  // per-call work space
+  gpb::DevBuf params;            // ell[d] | sf2, sn2   (per batch entry)
+  gpb::DevBuf XsT, sq, ZsT, zsq, Zd;
+  gpb::DevBuf A, Dinv, diag, info, scal, outv;
+  gpb::DevBuf aux0, aux1, aux2;  // stage-specific (gradient / Laplace) scratch
+  double* h_pinned = nullptr;    // pinned staging for small H2D/D2H
+  size_t h_pinned_bytes = 0;
+
+  std::vector<cudaEvent_t> ev_pool;   // ordering events for the look-ahead
+  size_t ev_next = 0;
+  cudaEvent_t tev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+  // Laplace state kept for prediction
+  int64_t lap_n = 0;
+
+  cudaEvent_t next_event();
+  double* pinned(size_t bytes);
+};
+
+namespace gpb {
+
+void make_tensor_map(CUtensorMap* map, const double* base, int64_t cols, int64_t rows, int64_t batch,
+                     int64_t row_pitch_elems, int64_t batch_pitch_elems);
+
+// Blocked right-looking Cholesky sweep (see chol.cu).  factor == true: factor the symmetric part
+// and carry the extra rows along; factor == false: the symmetric part already holds L (and Dinv
+// its inverted diagonal tiles) and only the extra rows are swept (X <- X L^-T).
+void chol_sweep(gpb_handle* h, FactorMat& m, bool factor);
+
+// fills m.mapA / m.mapD from the pointers and extents
+void finalize_factor_mat(FactorMat& m);
+
+}  // namespace gpb

@@ -1,0 +1,87 @@
+// gpb_kernels.cuh - launch interfaces of the sm_100a kernels of libgpb200.
+#pragma once
+#include "gpb_common.cuh"
+
+namespace gpb {
+
+// ---------------------------------------------------------------------------------------
+// TMA-fed FP64 DMMA "NT" tile kernel:  C(it,jt) (op)= sum_k A(it, k) * B(jt, k)^T
+// on 128x128 tiles of row-major matrices.  One CTA per tile; blockIdx.y = batch entry.
+// ---------------------------------------------------------------------------------------
+struct GemmArgs {
+  double* C;                // output matrix base
+  int64_t ldc;              // leading dimension of C (elements, even)
+  int64_t c_batch_stride;   // elements between batch entries of C
+  int rows_total;           // rows >= rows_total are never stored
+  // tile region.  tri == 1: columns jt in [j0, j1), rows it in [jt + i_off, R) (a trapezoid,
+  // enumerated column by column).  tri == 0: rows it in [i0, R) for every column.
+  int j0, j1, R, tri, i_off, i0;
+  // operands.  A slab s: mapA box at (ka0 + 16 s, 128 it, batch);
+  //            B slab s: mapB box at (kb0 + 16 s, b_row0 + 128 jt, batch).
+  int ka0, kb0, nk, b_row0;
+  int epi;                  // 0: C = acc     1: C = C - acc
+  int ntiles;               // gridDim.x
+};
+int gemm_region_tiles(const GemmArgs& a);       // host: number of tiles of the region
+void launch_dmma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmArgs a, int batch,
+                      cudaStream_t st);
+void dmma_gemm_init();                           // sets the dynamic smem attribute once
+
+// ---------------------------------------------------------------------------------------
+// Diagonal-tile factorisation: L = chol(A_kk) in place (lower), W = L^-1 to Dinv[k] (dense
+// 128x128, upper part zero), diag(L) to diag[k*128..], first failing pivot to *info.
+// ---------------------------------------------------------------------------------------
+struct TilePotrfArgs {
+  double* A;
+  int64_t lda, a_batch_stride;
+  int k;                    // tile index on the diagonal
+  double* Dinv;             // per batch: nt*128 rows x 128 cols
+  int64_t d_batch_stride;
+  double* diag;             // per batch: n_pad doubles
+  int64_t diag_batch_stride;
+  int* info;                // per batch: first failing pivot (1-based global index), 0 = ok
+};
+void launch_tile_potrf_inv(TilePotrfArgs a, int batch, cudaStream_t st);
+void tile_potrf_init();
+
+// ---------------------------------------------------------------------------------------
+// SE-ARD covariance assembly
+// ---------------------------------------------------------------------------------------
+// XsT[d][i] = X[i][d] / ell[d] (d-major, pitch ld_t), sq[i] = sum_d Xs^2 (same FMA chain as the
+// tile kernel's dot product, so the expanded-form distance of a point to itself is exactly 0).
+void launch_se_prep(const double* X, int64_t n, int d, const double* ell_dev, double* XsT,
+                    int64_t ld_t, double* sq, int batch, int64_t ell_batch_stride,
+                    int64_t xs_batch_stride, int64_t sq_batch_stride, cudaStream_t st);
+struct SeArgs {
+  const double* rT;  int64_t r_ld;  const double* r_sq;  int64_t n_rows_valid;  // row points
+  const double* cT;  int64_t c_ld;  const double* c_sq;  int64_t n_cols_valid;  // column points
+  int64_t xs_batch_stride, sq_batch_stride;      // per-batch strides of the scaled points
+  int d;
+  double* out; int64_t ld; int64_t out_batch_stride;
+  int64_t rows_pad, cols_pad;     // extent written (multiples of 64); beyond *_valid: identity / 0
+  const double* hyp_dev;          // per batch: [sf2, sn2]
+  int mode;                       // 0: symmetric, write both triangles  1: symmetric, lower tiles only
+                                  // 2: rectangular (no noise term, pad = 0)
+                                  // 3: rectangular, raw squared distances (no exp)
+  int clip;                       // 1: clamp r^2 at 0 (GPy RBF semantics)
+};
+void launch_se_build(const SeArgs& a, int batch, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------
+// finishing reductions (deterministic: fixed-order tree, no atomics)
+// ---------------------------------------------------------------------------------------
+// out[b] = 0.5*sum(z^2) + sum(log diag) + 0.5*n_valid*log(2 pi)
+void launch_nlml_finish(const double* z, int64_t z_batch_stride, const double* diag,
+                        int64_t diag_batch_stride, int64_t n_pad, int64_t n_valid, double* out,
+                        int batch, cudaStream_t st);
+// mean[i] = VT[i,:] . z ; var[i] = sf2 - |VT[i,:]|^2   (VT rows have pitch ld)
+void launch_predict_finish(const double* VT, int64_t ld, const double* z, int64_t n_pad, int64_t m,
+                           const double* hyp_dev, double* mean, double* var, cudaStream_t st);
+// generic helpers
+void launch_fill(double* p, int64_t n, double v, cudaStream_t st);
+void launch_copy_sub_mean(double* dst, const double* src, int64_t n, double mean, cudaStream_t st);
+
+// micro-benchmarks (kind 0: DMMA, 1: DFMA): returns flops executed; caller times it
+double launch_microbench(int kind, double* sink, cudaStream_t st);
+
+}  // namespace gpb

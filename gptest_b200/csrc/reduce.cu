@@ -1,0 +1,104 @@
+// reduce.cu - finishing reductions of the regression path (deterministic fixed-order trees).
+#include "gpb_kernels.cuh"
+
+namespace gpb {
+
+// fixed-order block reduction: every thread's partial goes through the same tree every run
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int t = threadIdx.x;
+  sh[t] = v;
+  __syncthreads();
+#pragma unroll
+  for (int s = NT / 2; s > 0; s >>= 1) {
+    if (t < s) sh[t] += sh[t + s];
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+// GPr.py:65-68: err_y = 0.5 y' K^-1 y = 0.5 |L^-1 y|^2 ; det = sum(log(diag(L))) ; n log(2 pi)/2
+__global__ void __launch_bounds__(512) nlml_finish_kernel(const double* __restrict__ z, int64_t z_bs,
+                                                          const double* __restrict__ diag, int64_t d_bs,
+                                                          int64_t n_pad, int64_t n_valid,
+                                                          double* __restrict__ out) {
+  __shared__ double sh[512];
+  const int b = blockIdx.x;
+  const double* zb = z + b * z_bs;
+  const double* db = diag + b * d_bs;
+  double q = 0.0, l = 0.0;
+  for (int64_t i = threadIdx.x; i < n_pad; i += 512) {
+    const double zi = zb[i];
+    q = fma(zi, zi, q);
+    l += log(db[i]);
+  }
+  const double qs = block_sum<512>(q, sh);
+  const double ls = block_sum<512>(l, sh);
+  if (threadIdx.x == 0) out[b] = 0.5 * qs + ls + 0.5 * static_cast<double>(n_valid) * 1.8378770664093453;
+}
+
+void launch_nlml_finish(const double* z, int64_t z_bs, const double* diag, int64_t d_bs, int64_t n_pad,
+                        int64_t n_valid, double* out, int batch, cudaStream_t st) {
+  nlml_finish_kernel<<<batch, 512, 0, st>>>(z, z_bs, diag, d_bs, n_pad, n_valid, out);
+  GPB_CUDA(cudaGetLastError());
+}
+
+// GPr.py:50-53 with V^T = Kzx L^-T and z = L^-1 y:  fz = V^T z,  cov = sf2 - rowsum(V^T * V^T)
+__global__ void __launch_bounds__(256) predict_finish_kernel(const double* __restrict__ VT, int64_t ld,
+                                                             const double* __restrict__ z, int64_t n_pad,
+                                                             const double* __restrict__ hyp,
+                                                             double* __restrict__ mean, double* __restrict__ var) {
+  __shared__ double sh[256];
+  const int64_t i = blockIdx.x;
+  const double* row = VT + i * ld;
+  double m = 0.0, s = 0.0;
+  for (int64_t j = 2 * threadIdx.x; j < n_pad; j += 512) {
+    const double2 v = *reinterpret_cast<const double2*>(row + j);
+    const double2 zz = *reinterpret_cast<const double2*>(z + j);
+    m = fma(v.x, zz.x, m);
+    m = fma(v.y, zz.y, m);
+    s = fma(v.x, v.x, s);
+    s = fma(v.y, v.y, s);
+  }
+  const double ms = block_sum<256>(m, sh);
+  const double ss = block_sum<256>(s, sh);
+  if (threadIdx.x == 0) {
+    mean[i] = ms;
+    var[i] = hyp[0] - ss;
+  }
+}
+
+void launch_predict_finish(const double* VT, int64_t ld, const double* z, int64_t n_pad, int64_t m,
+                           const double* hyp_dev, double* mean, double* var, cudaStream_t st) {
+  if (m == 0) return;
+  predict_finish_kernel<<<static_cast<unsigned>(m), 256, 0, st>>>(VT, ld, z, n_pad, hyp_dev, mean, var);
+  GPB_CUDA(cudaGetLastError());
+}
+
+__global__ void fill_kernel(double* p, int64_t n, double v) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    p[i] = v;
+}
+void launch_fill(double* p, int64_t n, double v, cudaStream_t st) {
+  if (n <= 0) return;
+  const int blocks = static_cast<int>((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  fill_kernel<<<blocks, 256, 0, st>>>(p, n, v);
+  GPB_CUDA(cudaGetLastError());
+}
+
+__global__ void copy_sub_mean_kernel(double* dst, const double* src, int64_t n, double mean) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = src[i] - mean;
+}
+void launch_copy_sub_mean(double* dst, const double* src, int64_t n, double mean, cudaStream_t st) {
+  if (n <= 0) return;
+  const int blocks = static_cast<int>((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  copy_sub_mean_kernel<<<blocks, 256, 0, st>>>(dst, src, n, mean);
+  GPB_CUDA(cudaGetLastError());
+}
+
+}  // namespace gpb

@@ -1,0 +1,138 @@
+/*
+ * gpb200.h - C ABI of libgpb200.so: the B200 (sm_100a) Gaussian-process inference hot path
+ * behind the GPtest Python API.
+ *
+ * The reference (osurdml/GPtest) has no FFI: its boundary is the Python module API of GPr.py,
+ * GPc.py and GPpref.py.  Each entry point below is what a ctypes binding of one reference
+ * method needs; the reference method it replaces is cited as file:line into the reference.
+ * gptest_b200/{GPr,GPc,GPpref}.py are those bindings.
+ *
+ * Conventions
+ *   - every function returns 0 on success, < 0 on argument / CUDA errors (text through
+ *     gpb_last_error), and reports numerical failure LAPACK-style through *info
+ *     (info > 0: leading minor of that order is not positive definite) so that the Python side
+ *     can raise numpy.linalg.LinAlgError exactly where the reference does (GPr.py:62,
+ *     GPpref.py:126-135);
+ *   - all matrices are fp64, row-major (numpy C order), sizes are in elements;
+ *   - "host" pointers are ordinary process memory, copied inside the call; pointers named
+ *     *_dev are CUDA device pointers on the handle's device;
+ *   - one handle = one device + one stream; calls on a handle are serialised by the caller;
+ *   - host-pointer calls return after their results are in host memory;
+ *   - there is no CPU fallback anywhere: without a CUDA device gpb_create fails.
+ */
+#ifndef GPB200_H
+#define GPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpb_handle gpb_handle;
+
+/* ---- lifecycle ------------------------------------------------------------------------ */
+int gpb_version(void);
+/* The handle owns a private stream; gpb_set_stream adopts a caller stream instead (a
+ * cudaStream_t such as torch.cuda.current_stream().cuda_stream; 0 = the legacy default stream).
+ * All kernels of the handle are ordered on that stream; gpb_get_stream returns it so that the
+ * caller can record CUDA events on it. */
+int gpb_create(int device, gpb_handle** out);
+int gpb_set_stream(gpb_handle* h, void* stream);
+void* gpb_get_stream(gpb_handle* h);
+int gpb_destroy(gpb_handle* h);
+const char* gpb_last_error(gpb_handle* h);            /* h may be NULL: last create error */
+/* tunables: "lookahead" (0/1), "nb_tiles" (outer block = nb_tiles*128 columns: 1,2,4),
+ * "batch_chunk" (problems resident at once in the batched path).  Returns <0 if unknown. */
+int gpb_set_option(gpb_handle* h, const char* name, int64_t value);
+/* stage times (ms) of the last GPr/potrf call measured with CUDA events on the handle's
+ * stream: [0]=covariance assembly [1]=factorisation (+fused forward solves)
+ * [2]=reductions/finish [3]=gradient stage [4]=whole device section.  n <= 8. */
+int gpb_get_timings(gpb_handle* h, float* ms, int n);
+/* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
+int64_t gpb_launch_count(gpb_handle* h);
+
+/* ---- training data: GaussianProcess.__init__ (GPr.py:17-42) stores trainInput/Target --- */
+int gpb_set_train(gpb_handle* h, const double* X, int64_t n, int32_t d, const double* y);
+int gpb_set_train_dev(gpb_handle* h, const double* X_dev, int64_t n, int32_t d, const double* y_dev);
+
+/* ---- covariance assembly ---------------------------------------------------------------
+ * SquaredExponential.compute_Kxx_matrix (GPr.py:99-103): sn2*I + sf2*exp(-0.5*sqdist(x/l,x/l)),
+ * full symmetric n x n.  khyp = [l_1..l_D, sf2, sn2]: the NATURAL parameters exactly as
+ * SquaredExponential.__init__ derives them on the host (GPr.py:93-97: hyp = exp(logHyp),
+ * M = hyp[:n-2], sf2 = hyp[n-2]**2, sn2 = hyp[n-1]**2) - the binding keeps those three lines so
+ * that the attributes .hyp/.M/.sf2/.sn2 stay bit-identical to the reference's.
+ * flags bit0: clip r^2 at 0 and force a zero diagonal distance (GPy RBF semantics, GPpref.py:122);
+ * out_is_dev != 0: K_out is a device pointer (n*n doubles). */
+int gpb_se_ard_kxx(gpb_handle* h, const double* khyp, double* K_out, int32_t out_is_dev, int32_t flags);
+/* SquaredExponential.compute_Kxz_matrix (GPr.py:105-110): n x m, no noise. Z is host (m x d). */
+int gpb_se_ard_kxz(gpb_handle* h, const double* khyp, const double* Z, int64_t m,
+                   double* Kxz_out, int32_t out_is_dev);
+
+/* squared_distance(A, B) (GPr.py:4-13) between the training inputs (A, n x d) and B (m x d, host):
+ * |a|^2 + |b|^2 - 2ab, n x m to host memory. */
+int gpb_sqdist(gpb_handle* h, const double* B, int64_t m, double* out);
+
+/* ---- regression -------------------------------------------------------------------------
+ * GaussianProcess.compute_likelihood (GPr.py:57-69): nlml = 0.5 (y-m)' K^-1 (y-m) +
+ * sum(log diag L) + n/2 log(2 pi).  grad (d+2 doubles, may be NULL): d nlml / d loghyp
+ * w.r.t. the LOG hyper-parameters [log l_1..l_D, log sf, log sn] (the value+gradient GPy's
+ * optimiser consumes in GP_parameter_fit.py:32-33). */
+int gpb_gpr_nlml(gpb_handle* h, const double* khyp, double mean, double* nlml,
+                 double* grad, int32_t* info);
+/* GaussianProcess.compute_prediction (GPr.py:45-54): fz = Kzx K^-1 y, cov = sf2 - diag(Kzx K^-1 Kxz)
+ * for m test points Z (host, m x d); outputs host arrays of m doubles. */
+int gpb_gpr_predict(gpb_handle* h, const double* khyp, double mean, const double* Z, int64_t m,
+                    double* fz, double* cov, int32_t* info);
+/* B independent evaluations of compute_likelihood on the same (X, y) with different
+ * hyper-parameters (the grid / multi-start fits GP_parameter_fit.py:32-33 runs one by one).
+ * loghyp: B x (d+2) host; nlml: B host; grad: B x (d+2) host or NULL; info: B host. */
+int gpb_gpr_nlml_batched(gpb_handle* h, const double* khyp, int64_t B, double mean,
+                         double* nlml, double* grad, int32_t* info);
+
+/* ---- dense factorisation on caller-owned device memory (np.linalg.cholesky, GPr.py:62) ---
+ * In-place lower Cholesky of the n x n row-major matrix A_dev (leading dimension lda >= n,
+ * n % 128 == 0, lda % 2 == 0); only the lower triangle is read and written. */
+int gpb_potrf_lower_dev(gpb_handle* h, double* A_dev, int64_t n, int64_t lda, int32_t* info);
+/* Same on a host matrix of any n (copied, padded, factored, lower triangle copied back,
+ * strict upper triangle zeroed like numpy). */
+int gpb_potrf_lower(gpb_handle* h, double* A, int64_t n, int32_t* info);
+/* C (M x N, ldc) = beta*C + alpha * A (M x K, lda) * B (N x K, ldb)^T on device memory through
+ * the TMA-fed DMMA tile kernel; M, N, K multiples of 128, alpha/beta in {(1,0), (-1,1)}.
+ * Test / bench hook for the kernel the factorisation spends its time in. */
+int gpb_dgemm_nt_dev(gpb_handle* h, double* C_dev, int64_t ldc, const double* A_dev, int64_t lda,
+                     const double* B_dev, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                     double alpha, double beta);
+
+/* ---- binary classification (GPc.py intent; R&W Alg. 3.1 / 3.2) ---------------------------
+ * labels y in {-1,+1} (host, n), khyp = [l_1..l_D, sf2], link 0 = probit (GPc.py:21),
+ * 1 = logit (GPc.py:17-19).  f_inout: start (if use_f0) and result mode (n).
+ * trace (2*max_iter doubles or NULL): (f_error, objective) per iteration. */
+int gpb_gpc_laplace(gpb_handle* h, const double* y, const double* khyp, int32_t link,
+                    double delta_f, int32_t max_iter, int32_t use_f0, double* f_inout,
+                    double* lml, int32_t* iters, double* trace, double* jitter, int32_t* info);
+int gpb_gpc_predict(gpb_handle* h, const double* Z, int64_t m, double* mu, double* var, double* prob);
+
+/* ---- pairwise preferences ----------------------------------------------------------------
+ * PreferenceGaussianProcess.calc_laplace (GPpref.py:112-157).  uvi: P x 2 int64 item indices
+ * (column 0 = u, column 1 = v), y: P labels in {-1,+1}, khyp = [l_1..l_D, variance] as the
+ * binding sets them on the kernel (GPpref.py:113-114).  grad_mode 0 = the reference's last-write-wins gradient (GPpref.py:77-78),
+ * 1 = accumulate (true Newton).  sigma is the probit noise actually used (1.0 reproduces the
+ * reference, GPpref.py:115).  The loop runs on the device until max|f_new - f| <= delta_f or
+ * max_iter; trace gets (f_error, lml) per iteration like the reference's print (GPpref.py:154). */
+int gpb_pref_laplace(gpb_handle* h, const int64_t* uvi, const double* y, int64_t P,
+                     const double* khyp, double sigma, double delta_f, int32_t max_iter,
+                     int32_t grad_mode, int32_t use_f0, double* f_inout, double* lml,
+                     int32_t* iters, double* trace, double* jitter, int32_t* info);
+/* PrefProbit.derivatives (GPpref.py:68-88) on its own: dense W (n x n) and gradient (n). */
+int gpb_pref_derivatives(gpb_handle* h, const int64_t* uvi, const double* y, int64_t P, int64_t n,
+                         const double* f, double sigma, int32_t grad_mode, double* W_out, double* g_out);
+
+/* ---- micro-benchmarks used by bench.py / tools to fix the roofline denominators ---------- */
+/* kind 0: DMMA.8x8x4 issue rate, 1: DFMA rate; returns TFLOP/s */
+int gpb_microbench(gpb_handle* h, int32_t kind, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPB200_H */

@@ -1,0 +1,152 @@
+"""CPU oracle for the preference-GP Laplace path (TEST INFRASTRUCTURE - not product code).
+
+Python-3 / numpy restatement of the reference's ``GPpref.py`` (which is Python 2 and imports
+the un-vendored GPy, so it cannot run here as-is).  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this file.
+
+Parity status
+  * Laplace loop, likelihood derivatives, log_marginal: PINNED - ``oracle/make_golden.py``
+    executes the reference's own ``GPpref.py`` source (its two py2 ``print`` statements
+    rewritten in memory, nothing else) and checks this restatement against it on the demo
+    data and on data with repeated items (KAT-3, KAT-4 in ``tests/golden/gppref_kat.npz``).
+  * Covariance matrix: PARITY UNPINNED - the reference obtains K from
+    ``GPy.kern.RBF(ARD=True).K`` (GPpref.py:109,122); GPy is a third-party dependency that
+    is absent from /root/reference and pinned nowhere (no requirements/lock file).
+    ``rbf_ard_K`` restates GPy's published RBF/Stationary algorithm from its documentation.
+
+The reference's quirks are reproduced on purpose:
+  1. gradient scatter with fancy-index ``+=`` : last write wins on repeated items
+     (GPpref.py:77-78), while W accumulates (GPpref.py:82-87);
+  2. ``calc_laplace`` overwrites the *method* ``set_sigma`` (GPpref.py:115) so the probit
+     sigma stays at its constructor value 1.0;
+  3. ``logdetK = sum(log(diag(L)))`` is half the log-determinant (GPpref.py:131) and is
+     halved again in ``log_marginal`` (GPpref.py:93).
+"""
+import numpy as np
+from scipy.special import ndtr
+
+_SQRT_2PI = np.sqrt(2 * np.pi)
+
+
+def std_norm_pdf(x):
+    """GPpref.py:7-10."""
+    x = np.clip(x, -1e150, 1e150)
+    return np.exp(-(x ** 2) / 2) / _SQRT_2PI
+
+
+def rbf_ard_K(x, lengthscale, variance):
+    """GPy ``RBF(ARD=True).K(X)`` restated (GPy Stationary._scaled_dist / RBF.K_of_r).
+
+    X is divided by the lengthscales; r2 = -2 X X^T + |X|^2 + |X|^2^T with the diagonal forced
+    to zero and negatives clipped to zero; r = sqrt(r2); K = variance * exp(-0.5 * r**2).
+    """
+    xs = np.asarray(x, dtype=float) / np.asarray(lengthscale, dtype=float)
+    xsq = np.sum(np.square(xs), axis=1)
+    r2 = -2.0 * np.dot(xs, xs.T) + (xsq[:, None] + xsq[None, :])
+    np.fill_diagonal(r2, 0.0)
+    r2 = np.clip(r2, 0, np.inf)
+    r = np.sqrt(r2)
+    return variance * np.exp(-0.5 * r ** 2)
+
+
+class ProbitPrefOracle:
+    """Restatement of ``PrefProbit`` (GPpref.py:46-94)."""
+
+    def __init__(self, sigma=1.0):
+        self.sigma = sigma                                   # GPpref.py:51-54
+        self.isqrt2sig = 1.0 / (sigma * np.sqrt(2.0))
+        self.i2var = self.isqrt2sig ** 2
+        self.log2pi = np.log(2.0 * np.pi)                    # GPpref.py:49
+
+    def z_k(self, uvi, f, y):
+        """GPpref.py:56-58: y * (f[v] - f[u]) / (sqrt(2) sigma); shapes (P,1)."""
+        return y * (self.isqrt2sig * (f[uvi[:, 1]] - f[uvi[:, 0]]))
+
+    def derivatives(self, uvi, y, f):
+        """GPpref.py:68-88 including the last-write-wins gradient (quirk 1)."""
+        nx = len(f)
+        z = self.z_k(uvi, f, y)
+        phi_z = ndtr(z)                                      # GPpref.py:71
+        n_z = std_norm_pdf(z)                                # GPpref.py:72
+        g = np.zeros((nx, 1), dtype=float)                   # GPpref.py:75
+        d = y * self.isqrt2sig * n_z / phi_z                 # GPpref.py:76
+        # GPpref.py:77-78.  ``a[idx] += v`` is ``a[idx] = a[idx] + v``: one gather, one add,
+        # one scatter; for a repeated index the LAST occurrence is the value that stays.
+        g[uvi[:, 0]] = g[uvi[:, 0]] - d
+        g[uvi[:, 1]] = g[uvi[:, 1]] + d
+        inner = -self.i2var * (z * n_z / phi_z + (n_z / phi_z) ** 2)   # GPpref.py:80
+        W = np.zeros((nx, nx), dtype=float)                  # GPpref.py:81
+        w = -inner[:, 0]                                     # W[..] -= ddpy_df  ==  += w
+        u, v = uvi[:, 0], uvi[:, 1]
+        # GPpref.py:82-87: sequential accumulation, pair by pair.  np.add.at is unbuffered
+        # and visits the operands in order, so every cell sees the same sequence of adds.
+        rows = np.stack([u, v, u, v], axis=1).ravel()        # per pair: (u,u) (v,v) (u,v) (v,u)
+        cols = np.stack([u, v, v, u], axis=1).ravel()
+        vals = np.stack([w, w, -w, -w], axis=1).ravel()
+        np.add.at(W, (rows, cols), vals)
+        return W, g
+
+    def log_marginal(self, uvi, y, f, iK, logdetK):
+        """GPpref.py:90-94 (quirk 3 lives in the caller's logdetK)."""
+        z = self.z_k(uvi, f, y)
+        phi_z = ndtr(z)
+        psi = (np.sum(np.log(phi_z)) - 0.5 * np.matmul(np.matmul(f.T, iK), f)
+               - 0.5 * logdetK - iK.shape[0] / 2.0 * self.log2pi)
+        return psi.flat[0]
+
+
+def gradient_last_writer(uvi, n):
+    """Index form of quirk 1, shared with the tests of the device kernel.
+
+    Returns (ku, kv): for every item i the index of the LAST pair whose u (resp. v) is i, or
+    -1.  The reference gradient is  g[i] = -d[ku[i]] (if any) + d[kv[i]] (if any).
+    """
+    ku = np.full(n, -1, dtype=np.int64)
+    kv = np.full(n, -1, dtype=np.int64)
+    ku[uvi[:, 0]] = np.arange(len(uvi))       # later assignments overwrite earlier ones
+    kv[uvi[:, 1]] = np.arange(len(uvi))
+    return ku, kv
+
+
+def calc_laplace(x, uvi, y, loghyp, delta_f=1e-6, f=None, max_iter=None, return_trace=False):
+    """``PreferenceGaussianProcess.calc_laplace`` (GPpref.py:112-157).
+
+    ``max_iter`` (not in the reference, which has no cap) bounds test/bench runs.
+    Returns (f (n,1), lml) and, with return_trace, the per-iteration (f_error, lml) list the
+    reference prints (GPpref.py:154).
+    """
+    x = np.asarray(x, dtype=float)
+    n, d = x.shape
+    y = np.asarray(y, dtype=float).reshape(-1, 1)
+    lik = ProbitPrefOracle()                                 # sigma = 1.0, never updated (quirk 2)
+    lengthscale = np.exp(loghyp[0:d])                        # GPpref.py:113
+    variance = (np.exp(loghyp[d])) ** 2                      # GPpref.py:114
+    if f is None:
+        f = np.zeros((n, 1))                                 # GPpref.py:117-118
+    Ix = np.eye(n)                                           # GPpref.py:121
+    K = rbf_ard_K(x, lengthscale, variance)                  # GPpref.py:122
+    eps = 1e-6                                               # GPpref.py:123
+    while True:                                              # GPpref.py:126-135
+        try:
+            L = np.linalg.cholesky(K + eps * Ix)
+            iK = np.linalg.solve(L.T, np.linalg.solve(L, Ix))
+            logdetK = np.sum(np.log(L.diagonal()))           # = 0.5*log|K| (quirk 3)
+            break
+        except np.linalg.LinAlgError:
+            eps = eps * 10
+    f_error = delta_f + 1                                    # GPpref.py:138
+    trace = []
+    lml = None
+    while f_error > delta_f:                                 # GPpref.py:140
+        W, g = lik.derivatives(uvi, y, f)                    # GPpref.py:141
+        G = iK + W                                           # GPpref.py:142
+        f_new = np.matmul(np.linalg.inv(G), np.matmul(W, f) + g)   # GPpref.py:143
+        lml = lik.log_marginal(uvi, y, f_new, iK, logdetK)   # GPpref.py:144
+        f_error = np.max(np.abs(f_new - f))                  # GPpref.py:151-152
+        trace.append((float(f_error), float(lml)))
+        f = f_new                                            # GPpref.py:155
+        if max_iter is not None and len(trace) >= max_iter:
+            break
+    if return_trace:
+        return f, lml, trace
+    return f, lml
