@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py - GP fits/sec at N=16384 fp64 (kernel + Cholesky + solve + LML) and Cholesky TFLOP/s.
+
+One "step" = one evaluation of GaussianProcess.compute_likelihood (GPr.py:57-69) on BASELINE
+config 2: N = 16384, D = 8 SE-ARD, synthetic targets (SURVEY section 8d recipe).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+* value    : fits/s with X, y resident in HBM (only the 10 hyper-parameters go up and one double
+             comes back per step), timed with CUDA events on the launching stream.
+* e2e      : the same metric through the drop-in API, GPr.GaussianProcess(...).compute_likelihood(hyp),
+             with X and y in pinned HOST memory: every step uploads them and reads the result back.
+* roofline : the factorisation stage (>= 99 % of it is the TMA-fed DMMA tile kernel), N^3/3 flops over
+             its CUDA-event duration, against the FP64 tensor pipe rate measured in the same run
+             (MEASURED_PEAKS.json has no fp64 entry; cuBLAS DGEMM is reported beside it).
+* N > 1    : the path shards over independent problems (hyper-parameter vectors): every rank fits its
+             own slice, no data-path collective; the scalar likelihoods are all-gathered over NCCL
+             after the timed region ("weak" scaling: K fits per GPU).
+* --impl reference : the reference's own CPU arithmetic (oracle/gpr_oracle.py, a line-by-line port of
+             GPr.py verified bit-for-bit against it) on the host cores, on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FIT, D_FIT, M_TEST = 16384, 8, 1024
+METRIC = "GP fits/sec at N=16384 fp64 (kernel+Cholesky+solve+LML)"
+WORKLOAD = "GPr N=16384 D=8 SE-ARD fp64 compute_likelihood (BASELINE configs[1])"
+
+
+def make_c2(n=N_FIT, d=D_FIT):
+    """SURVEY 8(d) C2 recipe."""
+    rng = np.random.default_rng(0)
+    X = rng.random((n, d))
+    w = rng.standard_normal(d)
+    y = np.sin(X @ w) + 0.1 * rng.standard_normal(n)
+    Z = rng.random((M_TEST, d))
+    log_hyp = np.log([0.5] * d + [1.0, 0.1])
+    return X, y, Z, log_hyp
+
+
+def make_c5(n=2048, B=1024):
+    """SURVEY 8(d) C5 recipe: GP_parameter_fit.py:9-28 data, 32x32 hyper-parameter grid."""
+    rng = np.random.default_rng(0)
+    X = 100 * rng.random((n, 2))
+    a, b = X[:, 0], X[:, 1]
+    cost = 3.0 + 10 * np.exp(-np.sqrt((a - 40) ** 2 + (b - 40) ** 2) / 16) \
+        + 7 * np.exp(-np.sqrt((a - 10) ** 2 + (b - 90) ** 2) / 12) \
+        + 4 * np.exp(-np.sqrt((a - 80) ** 2 + (b - 60) ** 2) / 32) \
+        + 7 * np.exp(-np.sqrt((a + 20) ** 2 + (b - 50) ** 2) / 32) \
+        + 7 * np.exp(-np.sqrt((a - 120) ** 2 + (b - 50) ** 2) / 32) \
+        + 12 * np.exp(-np.sqrt((a - 80) ** 2 + (b - 20) ** 2) / 8) \
+        + 5 * np.exp(-np.sqrt((a - 60) ** 2 + (b - 80) ** 2) / 10) \
+        + 3 * np.exp(-np.sqrt((a - 90) ** 2 + (b - 90) ** 2) / 20)
+    Y = cost + 0.25 * rng.standard_normal(n) - 3.0
+    g = int(round(np.sqrt(B)))
+    ll = np.linspace(np.log(2), np.log(200), g)
+    lf = np.linspace(np.log(0.3), np.log(30), g)
+    L, F = np.meshgrid(ll, lf, indexing='ij')
+    lh = np.stack([L.ravel(), L.ravel(), F.ravel(), np.full(g * g, np.log(0.25))], axis=1)[:B]
+    return X, Y, lh
+
+
+def khyp_of(log_hyp):
+    h = np.exp(np.asarray(log_hyp, dtype=float))
+    return np.concatenate([h[:-2], [h[-2] ** 2, h[-1] ** 2]])
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_fit_seconds(n, log_hyp, X, y):
+    from oracle import gpr_oracle
+    t0 = time.perf_counter()
+    v = gpr_oracle.nlml(log_hyp, X[:n], y[:n])
+    return time.perf_counter() - t0, float(v[0, 0])
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        info = threadpool_info()
+        ths = [i.get('num_threads') for i in info if i.get('user_api') == 'blas']
+        if ths:
+            return int(max(ths))
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def cpu_baseline(budget_s=20.0):
+    """The reference's arithmetic (oracle port of GPr.py:57-69) on the host cores, bounded sample."""
+    X, y, _, lh = make_c2()
+    t1024, _ = cpu_fit_seconds(1024, lh, X, y)
+    t1024, _ = cpu_fit_seconds(1024, lh, X, y)
+    ns = 1024
+    for cand in (2048, 4096, 8192):
+        if t1024 * (cand / 1024.0) ** 3 <= budget_s:
+            ns = cand
+    t, _ = cpu_fit_seconds(ns, lh, X, y) if ns > 1024 else (t1024, 0)
+    scale = (N_FIT / ns) ** 3
+    return {"value": 1.0 / (t * scale), "unit": "fits/s", "cores": blas_threads(), "kind": "port",
+            "sample": "one compute_likelihood at N=%d (first %d points of the workload), %.2f s; "
+                      "extrapolated x(16384/%d)^3 = %.0f for N=16384" % (ns, ns, t, ns, scale),
+            "host_cpus": os.cpu_count()}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    X, y, _, lh = make_c2()
+    steps, warm = args.steps, args.warmup
+    t1024, _ = cpu_fit_seconds(1024, lh, X, y)
+    t1024, _ = cpu_fit_seconds(1024, lh, X, y)
+    ns = 1024
+    for cand in (2048, 4096):
+        if t1024 * (cand / 1024.0) ** 3 * (steps + warm) <= 150.0:
+            ns = cand
+    for _ in range(warm):
+        cpu_fit_seconds(ns, lh, X, y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_fit_seconds(ns, lh, X, y)
+    el = time.perf_counter() - t0
+    scale = (N_FIT / ns) ** 3
+    per_fit = el / steps * scale
+    val = 1.0 / per_fit
+    sample = ("each step = one compute_likelihood of the oracle port of GPr.py:57-69 at N=%d (first %d points), "
+              "%.3f s/step measured, extrapolated x%.0f (cubic) to N=16384" % (ns, ns, el / steps, scale))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "fits/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": per_fit * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n": N_FIT, "d": D_FIT},
+            "cpu_baseline": {"value": val, "unit": "fits/s", "cores": blas_threads(), "kind": "port", "sample": sample,
+                             "host_cpus": os.cpu_count()},
+            "e2e": {"value": val, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from gptest_b200 import _lib, GPr
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _lib.set_default_device(local_rank)
+    h = _lib.default_handle(local_rank)
+    h.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    X, y, Z, lh = make_c2()
+    steps, warm = args.steps, args.warmup
+    # every rank owns its own slice of hyper-parameter vectors (independent fits)
+    rng = np.random.default_rng(1000 + rank)
+    lhs = lh[None, :] + 0.05 * rng.standard_normal((steps + warm, lh.size))
+    lhs[0] = lh
+    khs = np.array([khyp_of(l) for l in lhs])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm ----------------
+    h.set_train(X, y)
+    for i in range(warm):
+        h.gpr_nlml(khs[i])
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = h.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    vals, stage = [], {"kbuild_ms": 0.0, "factor_ms": 0.0, "finish_ms": 0.0, "total_ms": 0.0}
+    ev0.record()
+    for i in range(steps):
+        vals.append(h.gpr_nlml(khs[warm + i]))
+        tm = h.timings()
+        for k in stage:
+            stage[k] += tm[k]
+    ev1.record()
+    barrier()
+    launches = h.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = t.item()
+    for k in stage:
+        stage[k] /= steps
+
+    # ---------------- end-to-end arm: drop-in API, host buffers ----------------
+    Xp = torch.from_numpy(X).pin_memory().numpy()
+    yp = torch.from_numpy(y).pin_memory().numpy()
+    gp = GPr.GaussianProcess(lh, 0, 0, "SE", "zero", "zero", Xp, yp)
+    e_steps = max(3, min(steps, 10))
+    for i in range(2):
+        gp.compute_likelihood(lhs[i])
+    barrier()
+    ev0.record()
+    for i in range(e_steps):
+        out = gp.compute_likelihood(lhs[warm + (i % steps)])
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device='cuda')
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item() / e_steps
+    assert abs(out[0, 0] - vals[(e_steps - 1) % steps]) <= 1e-9 * abs(out[0, 0])
+
+    # ---------------- gather the scalar likelihoods (the only collective) ----------------
+    v = torch.tensor(vals, dtype=torch.float64, device='cuda')
+    if dist is not None:
+        allv = [torch.empty_like(v) for _ in range(world)]
+        dist.all_gather(allv, v)
+        v = torch.cat(allv)
+    all_vals = v.cpu().numpy()
+
+    extra = {}
+    if rank == 0 and world == 1 and not args.skip_extras:
+        extra = single_gpu_extras(h, X, y, Z, lh)
+    if args.sweep:
+        extra["sweep_1024x2048"] = sweep_c5(h, rank, world, dist, torch)
+
+    if rank == 0:
+        fits_per_s = world * steps / (ms_max * 1e-3)
+        flops_chol = N_FIT ** 3 / 3.0
+        chol_tflops = flops_chol / (stage["factor_ms"] * 1e-3) / 1e12
+        dmma_peak = h.microbench(0)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dmma_gemm_dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": fits_per_s, "unit": "fits/s", "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n": N_FIT, "d": D_FIT, "parallelism": "independent fits per GPU (dp%d)" % world,
+                       "l2": "working set 2 GiB per fit > 126 MB L2 (no flush needed)", "fits_per_gpu": steps},
+            "cholesky_fp64_tflops": chol_tflops,
+            "stage_ms": stage,
+            "roofline": {"bound": "tensor", "achieved": chol_tflops, "peak": dmma_peak, "unit": "TFLOP/s",
+                         "frac": chol_tflops / dmma_peak, "traffic": traffic,
+                         "kernel": "dmma_gemm_nt_kernel inside the factorisation stage (N^3/3 flop / CUDA-event stage time, panels included)",
+                         "peak_source": "FP64 DMMA.8x8x4 pipe rate measured in this run (gpb_microbench); MEASURED_PEAKS.json has no fp64 entry; nominal 37 TFLOP/s",
+                         "peak_cublas_dgemm": extra.get("cublas_dgemm_8192_tflops")},
+            "roofline_kbuild": {"bound": "hbm", "achieved": extra.get("kxx_full_GBs"), "peak": hbm_peak, "unit": "GB/s",
+                                "frac": (extra.get("kxx_full_GBs") / hbm_peak) if extra.get("kxx_full_GBs") else None,
+                                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                                "bytes": 8.0 * N_FIT * N_FIT + 8.0 * N_FIT * D_FIT},
+            "e2e": {"value": world / (e2e_ms * 1e-3), "unit": "fits/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(X.nbytes + y.nbytes + 8 * (D_FIT + 2)), "d2h_bytes_per_step": 12,
+                    "api": "GPr.GaussianProcess.compute_likelihood(hyp), pinned host X/y uploaded every call"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "nlml_first": float(all_vals[0]), "nlml_count": int(all_vals.size),
+        }
+        line.update(extra)
+        if world == 1 and not args.skip_cpu:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def single_gpu_extras(h, X, y, Z, lh):
+    """secondary figures of the same run: cuBLAS bar, covariance-assembly bandwidth, predict."""
+    import torch
+    out = {}
+    kh = khyp_of(lh)
+    n = 8192
+    A = torch.randn(n, n, dtype=torch.float64, device='cuda')
+    B = torch.randn(n, n, dtype=torch.float64, device='cuda')
+    best = 1e30
+    for i in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); C = A @ B.T; e1.record(); torch.cuda.synchronize()
+        if i:
+            best = min(best, e0.elapsed_time(e1))
+    out["cublas_dgemm_8192_tflops"] = 2 * n ** 3 / best / 1e9
+    del A, B, C
+    K = torch.empty((N_FIT, N_FIT), dtype=torch.float64, device='cuda')
+    ts = []
+    for i in range(6):
+        h.kxx_dev(kh, K.data_ptr())
+        if i:
+            ts.append(h.timings()["kbuild_ms"])
+    out["kxx_full_ms"] = float(np.mean(ts))
+    out["kxx_full_GBs"] = (8.0 * N_FIT * N_FIT + 8.0 * N_FIT * D_FIT) / (out["kxx_full_ms"] * 1e-3) / 1e9
+    del K
+    h.set_train(X, y)
+    for i in range(3):
+        fz, cov = h.gpr_predict(kh, Z)
+    out["fit_predict_ms"] = h.timings()["total_ms"]
+    return out
+
+
+def sweep_c5(h, rank, world, dist, torch):
+    """BASELINE config 5: 1024 independent N=2048 problems, contiguous slices per rank (strong scaling)."""
+    X, Y, lhs = make_c5()
+    B = len(lhs)
+    lo, hi = rank * B // world, (rank + 1) * B // world
+    kh = np.array([khyp_of(l) for l in lhs[lo:hi]])
+    h.set_train(X, Y)
+    h.gpr_nlml_batched(kh[:min(len(kh), 32)])
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    vals, info = h.gpr_nlml_batched(kh)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+    v = torch.from_numpy(vals).cuda()
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        allv = [torch.empty_like(v) for _ in range(world)]
+        dist.all_gather(allv, v)
+        v = torch.cat(allv)
+    ms = t.item()
+    return {"problems": B, "n": 2048, "ms": ms, "fits_per_s": B / (ms * 1e-3),
+            "chol_tflops": B * 2048 ** 3 / 3.0 / (ms * 1e-3) / 1e12, "scaling": "strong",
+            "nlml_checksum": float(v.sum().item()), "failed": int((info != 0).sum())}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sweep", action="store_true", default=True, help="also time the 1024 x N=2048 sweep (config 5)")
+    ap.add_argument("--no-sweep", dest="sweep", action="store_false")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

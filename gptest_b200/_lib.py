@@ -245,10 +245,19 @@ class Handle:
 
 
 _default = {}
+_default_device = int(os.environ.get('GPB_DEVICE', os.environ.get('LOCAL_RANK', '0')))
 
 
-def default_handle(device=0):
+def set_default_device(device):
+    """Device used by the drop-in classes of this process (one process per GPU)."""
+    global _default_device
+    _default_device = int(device)
+
+
+def default_handle(device=None):
     """Process-wide handle per device, shared by the drop-in classes (work space is reused)."""
+    if device is None:
+        device = _default_device
     h = _default.get(device)
     if h is None:
         h = _default[device] = Handle(device)
