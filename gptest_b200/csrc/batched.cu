@@ -14,17 +14,6 @@ int gpr_nlml_grad_chunk(gpb_handle* h, const double* khyp, int64_t B, double mea
                         double* grad, int32_t* info);   // grad.cu
 }
 
-namespace {
-
-__global__ void set_y_rows_kernel(double* A, int64_t batch_stride, int64_t row_off, const double* y,
-                                  int64_t n, int64_t n_pad, double mean) {
-  double* dst = A + blockIdx.y * batch_stride + row_off;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n_pad;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    dst[i] = (i < n) ? y[i] - mean : 0.0;
-}
-
-}  // namespace
 
 extern "C" int gpb_gpr_nlml_batched(gpb_handle* h, const double* khyp, int64_t B, double mean, double* nlml,
                                     double* grad, int32_t* info) {
@@ -95,11 +84,7 @@ extern "C" int gpb_gpr_nlml_batched(gpb_handle* h, const double* khyp, int64_t B
       a.d = d; a.out = m.A; a.ld = np; a.out_batch_stride = m.batch_stride;
       a.rows_pad = a.cols_pad = np; a.hyp_dev = hyp2; a.mode = 1; a.clip = 0;
       launch_se_build(a, bc, h->s0);
-      {
-        dim3 grid(static_cast<unsigned>((np + 255) / 256), bc);
-        set_y_rows_kernel<<<grid, 256, 0, h->s0>>>(m.A, m.batch_stride, np * np, h->y.as<double>(), h->n, np, mean);
-        GPB_CUDA(cudaGetLastError());
-      }
+      launch_set_y_rows(m.A, m.batch_stride, np * np, h->y.as<double>(), h->n, np, mean, bc, h->s0);
       h->launches += 3;
       chol_sweep(h, m, true);
       launch_nlml_finish(m.A + np * np, m.batch_stride, m.diag, m.diag_bs, np, h->n, h->scal.as<double>(), bc, h->s0);

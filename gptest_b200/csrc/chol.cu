@@ -68,25 +68,33 @@ struct Sweep {
   FactorMat& m;
   bool factor;
   int nt, R;
+  int x0 = 0, xn = 0;     // non-factor mode: tile rows [x0, x0 + xn) are swept
+  bool grow = false;      // identity right-hand sides: tile row x0 + q is zero left of column q
 
-  GemmArgs base() const {
+  // last tile row (exclusive) that can be non-zero once tile column k has been processed
+  int r_at(int k) const {
+    if (factor) return R;
+    if (!grow) return x0 + xn;
+    return x0 + (k + 1 < xn ? k + 1 : xn);
+  }
+  GemmArgs base(int k) const {
     GemmArgs a{};
     a.C = m.A;
     a.ldc = m.ld;
     a.c_batch_stride = m.batch_stride;
     a.rows_total = static_cast<int>(m.rows_total);
-    a.R = R;
+    a.R = r_at(k);
     if (factor) {
       a.tri = 1;
     } else {
       a.tri = 0;
-      a.i0 = nt;
+      a.i0 = x0;
     }
     return a;
   }
   // A[i,k] <- A[i,k] * W_k^T for the rows below tile (k,k) (and the appended rows)
   void trsm(int k, cudaStream_t st) {
-    GemmArgs a = base();
+    GemmArgs a = base(k);
     a.j0 = k; a.j1 = k + 1; a.i_off = 1;
     a.ka0 = k * TILE; a.kb0 = 0; a.nk = TILE / GEMM_KB; a.b_row0 = 0;
     a.epi = 0;
@@ -97,7 +105,7 @@ struct Sweep {
   // A[i,j] -= sum_{k in [ka,kb)} A[i,k] A[j,k]^T for tile columns j in [c0,c1), rows i >= j
   void update(int c0, int c1, int ka, int kb, cudaStream_t st) {
     if (c1 <= c0 || kb <= ka) return;
-    GemmArgs a = base();
+    GemmArgs a = base(kb - 1);
     a.j0 = c0; a.j1 = c1; a.i_off = 0;
     a.ka0 = ka * TILE; a.kb0 = ka * TILE; a.nk = (kb - ka) * TILE / GEMM_KB; a.b_row0 = 0;
     a.epi = 1;
@@ -124,9 +132,19 @@ struct Sweep {
 }  // namespace
 
 void chol_sweep(gpb_handle* h, FactorMat& m, bool factor) {
+  SweepPlan plan;
+  plan.factor = factor;
+  chol_sweep(h, m, plan);
+}
+
+void chol_sweep(gpb_handle* h, FactorMat& m, const SweepPlan& plan) {
+  const bool factor = plan.factor;
   const int nt = static_cast<int>(m.n_pad / TILE);
   const int R = static_cast<int>((m.rows_total + TILE - 1) / TILE);
   Sweep s{h, m, factor, nt, R};
+  s.x0 = plan.extra_tile0 >= 0 ? plan.extra_tile0 : nt;
+  s.xn = plan.extra_tiles > 0 ? plan.extra_tiles : R - s.x0;
+  s.grow = plan.grow;
   const int nb = h->nb_tiles < 1 ? 1 : h->nb_tiles;
   // without a symmetric part to factor there is no panel critical path: plain order
   const bool la = h->lookahead && factor && m.batch == 1 && nt > nb;

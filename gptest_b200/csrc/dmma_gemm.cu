@@ -52,6 +52,9 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const int batch = blockIdx.y;
   int it, jt;
   decode_tile(p, blockIdx.x, it, jt);
+  const int ka0 = p.k_from_row ? it * TILE : p.ka0;
+  const int kb0 = p.k_from_row ? it * TILE : p.kb0;
+  const int nk = p.k_from_row ? (p.k_tiles - it) * (TILE / GEMM_KB) : p.nk;
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -68,15 +71,15 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     if (lane == 0) {
       tma_prefetch_desc(&mapA);
       tma_prefetch_desc(&mapB);
-      const int arow = it * TILE;
+      const int arow = p.a_row0 + it * TILE;
       const int brow = p.b_row0 + jt * TILE;
-      for (int s = 0; s < p.nk; ++s) {
+      for (int s = 0; s < nk; ++s) {
         const int st = s % GEMM_STAGES;
         if (s >= GEMM_STAGES) mbar_wait(&empty[st], ((s / GEMM_STAGES) - 1) & 1);
         uint8_t* dst = smem + st * GEMM_STAGE_BYTES;
         mbar_arrive_expect_tx(&full[st], GEMM_STAGE_BYTES);
-        tma_load_3d(dst, &mapA, &full[st], p.ka0 + GEMM_KB * s, arow, batch);
-        tma_load_3d(dst + TILE * GEMM_KB * 8, &mapB, &full[st], p.kb0 + GEMM_KB * s, brow, batch);
+        tma_load_3d(dst, &mapA, &full[st], ka0 + GEMM_KB * s, arow, batch);
+        tma_load_3d(dst + TILE * GEMM_KB * 8, &mapB, &full[st], kb0 + GEMM_KB * s, brow, batch);
       }
     }
     return;
@@ -117,7 +120,7 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  for (int s = 0; s < p.nk; ++s) {
+  for (int s = 0; s < nk; ++s) {
     const int st = s % GEMM_STAGES;
     mbar_wait(&full[st], (s / GEMM_STAGES) & 1);
     const uint8_t* sa = smem + st * GEMM_STAGE_BYTES;
@@ -194,7 +197,7 @@ void launch_dmma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmArgs
                       cudaStream_t st) {
   const int ntiles = gemm_region_tiles(a);
   GPB_REQUIRE(ntiles >= 0, "dmma_gemm: empty column in trapezoid region");
-  if (ntiles == 0 || a.nk == 0) return;
+  if (ntiles == 0 || (a.nk == 0 && !a.k_from_row)) return;
   a.ntiles = ntiles;
   dim3 grid(ntiles, batch, 1);
   dmma_gemm_nt_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(mapA, mapB, a);

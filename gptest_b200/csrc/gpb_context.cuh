@@ -92,6 +92,17 @@ void make_tensor_map(CUtensorMap* map, const double* base, int64_t cols, int64_t
 // and carry the extra rows along; factor == false: the symmetric part already holds L (and Dinv
 // its inverted diagonal tiles) and only the extra rows are swept (X <- X L^-T).
 void chol_sweep(gpb_handle* h, FactorMat& m, bool factor);
+struct SweepPlan {
+  bool factor = true;      // factor the symmetric part (appended rows ride along)
+  int extra_tile0 = -1;    // non-factor mode: first tile row swept (default: first row after the matrix)
+  int extra_tiles = 0;     // non-factor mode: number of tile rows swept (default: all appended rows)
+  bool grow = false;       // the swept block starts as the identity: tile row q is zero left of column q
+};
+void chol_sweep(gpb_handle* h, FactorMat& m, const SweepPlan& plan);
+
+// K^-1 on the lower tiles of the symmetric part from its factor (grad.cu); needs the buffer layout
+// rows [0,np) L | [np, np+128) appended tile row | [np+128, 2np+128) scratch for U = L^-T
+void chol_inverse_lower(gpb_handle* h, FactorMat& m);
 
 // fills m.mapA / m.mapD from the pointers and extents
 void finalize_factor_mat(FactorMat& m);

@@ -16,9 +16,11 @@ struct GemmArgs {
   // tile region.  tri == 1: columns jt in [j0, j1), rows it in [jt + i_off, R) (a trapezoid,
   // enumerated column by column).  tri == 0: rows it in [i0, R) for every column.
   int j0, j1, R, tri, i_off, i0;
-  // operands.  A slab s: mapA box at (ka0 + 16 s, 128 it, batch);
+  // operands.  A slab s: mapA box at (ka0 + 16 s, a_row0 + 128 it, batch);
   //            B slab s: mapB box at (kb0 + 16 s, b_row0 + 128 jt, batch).
-  int ka0, kb0, nk, b_row0;
+  // k_from_row != 0: the k range of tile (it, jt) starts at tile column `it` (operands that are
+  // upper triangular: U U^T products), i.e. ka0 = kb0 = 128 it and nk = 8 (k_tiles - it).
+  int ka0, kb0, nk, a_row0, b_row0, k_from_row, k_tiles;
   int epi;                  // 0: C = acc     1: C = C - acc
   int ntiles;               // gridDim.x
 };
@@ -78,6 +80,10 @@ void launch_nlml_finish(const double* z, int64_t z_batch_stride, const double* d
 void launch_predict_finish(const double* VT, int64_t ld, const double* z, int64_t n_pad, int64_t m,
                            const double* hyp_dev, double* mean, double* var, cudaStream_t st);
 // generic helpers
+void launch_set_y_rows(double* A, int64_t batch_stride, int64_t row_off, const double* y, int64_t n,
+                       int64_t n_pad, double mean, int batch, cudaStream_t st);
+void launch_row_dot(const double* M, int64_t ld, int64_t m_bs, const double* x, int64_t x_bs, int64_t nrows,
+                    int64_t ncols, int upper, double* out, int64_t out_bs, int batch, cudaStream_t st);
 void launch_fill(double* p, int64_t n, double v, cudaStream_t st);
 void launch_copy_sub_mean(double* dst, const double* src, int64_t n, double mean, cudaStream_t st);
 

@@ -77,6 +77,21 @@ void launch_predict_finish(const double* VT, int64_t ld, const double* z, int64_
   GPB_CUDA(cudaGetLastError());
 }
 
+// row `row_off / ld` of every batch entry <- y - mean (zero padded): the right-hand side stored as a row
+__global__ void set_y_rows_kernel(double* A, int64_t batch_stride, int64_t row_off, const double* y,
+                                  int64_t n, int64_t n_pad, double mean) {
+  double* dst = A + blockIdx.y * batch_stride + row_off;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n_pad;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = (i < n) ? y[i] - mean : 0.0;
+}
+void launch_set_y_rows(double* A, int64_t batch_stride, int64_t row_off, const double* y, int64_t n,
+                       int64_t n_pad, double mean, int batch, cudaStream_t st) {
+  dim3 grid(static_cast<unsigned>((n_pad + 255) / 256), batch);
+  set_y_rows_kernel<<<grid, 256, 0, st>>>(A, batch_stride, row_off, y, n, n_pad, mean);
+  GPB_CUDA(cudaGetLastError());
+}
+
 __global__ void fill_kernel(double* p, int64_t n, double v) {
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)

@@ -295,3 +295,38 @@ def test_full_size_fit_properties(handle):
     # |mean| < 1e-3 entries only measure cancellation noise of both solvers)
     assert np.abs(fz - mref).max() / np.abs(mref).max() < 1e-9
     assert np.abs(cov - vref).max() < 1e-9
+
+
+# ---------------------------------------------------------------------------------------
+# gradients (not in the reference: textbook formula, pinned by finite differences in test_oracle)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d", [(60, 3), (300, 1), (1000, 8), (1300, 2)])
+def test_nlml_gradient_matches_oracle(handle, n, d):
+    rng = np.random.default_rng(n + d)
+    x = rng.random((n, d))
+    y = np.sin(x @ rng.standard_normal(d)) + 0.1 * rng.standard_normal(n)
+    lh = np.log(np.r_[0.4 + 0.4 * rng.random(d), 1.1, 0.15])
+    handle.set_train(x, y)
+    v, g = handle.gpr_nlml(khyp_of(lh), want_grad=True)
+    ref = float(gpr_oracle.nlml(lh, x, y)[0, 0])
+    gref = gpr_oracle.nlml_grad(lh, x, y)
+    assert abs(v - ref) <= 1e-8 * abs(ref)
+    assert np.abs(g - gref).max() <= 1e-8 * np.abs(gref).max(), (g, gref)
+    assert v == handle.gpr_nlml(khyp_of(lh))          # the value is the same kernel sequence
+
+
+def test_batched_gradients_equal_single_calls(handle):
+    rng = np.random.default_rng(12)
+    n, d, B = 520, 2, 5
+    x = 100 * rng.random((n, d))
+    y = np.sin(x[:, 0] / 20) + 0.25 * rng.standard_normal(n)
+    handle.set_train(x, y)
+    lhs = np.log(np.c_[20 * np.exp(0.3 * rng.standard_normal((B, d))), np.sqrt(10) * np.ones(B), np.ones(B)])
+    kh = np.array([khyp_of(l) for l in lhs])
+    vals, grads, info = handle.gpr_nlml_batched(kh, want_grad=True)
+    assert (info == 0).all()
+    for b in range(B):
+        v, g = handle.gpr_nlml(kh[b], want_grad=True)
+        assert v == vals[b] and np.array_equal(g, grads[b])
+        gref = gpr_oracle.nlml_grad(lhs[b], x, y)
+        assert np.abs(grads[b] - gref).max() <= 1e-8 * np.abs(gref).max()
