@@ -1,1 +1,135 @@
-"""Drop-in replacement for the reference's ``GPpref.py`` (under construction in this commit)."""
+"""Drop-in replacement for the reference's ``GPpref.py`` with the numerics on a B200.
+
+Same public names and signatures as /root/reference/GPpref.py (cited per symbol);
+``GP_preference_demo.py:60,67`` and ``fmin(prefGP.calc_nlml, theta0)`` run unmodified.  The
+covariance assembly, the explicit inverse, every Newton iteration (likelihood derivatives, W,
+the dense solve) and the objective are CUDA kernels behind libgpb200's C ABI; the reference's
+GPy dependency is gone (``RBF`` below is a two-attribute stand-in whose ``K`` is the device
+kernel with GPy's RBF semantics).
+
+The reference's behaviour is reproduced on purpose, quirks included:
+last-write-wins gradient (GPpref.py:77-78), the probit sigma that never changes because
+``calc_laplace`` overwrites the method ``set_sigma`` (GPpref.py:115), and ``logdetK`` being half the
+log-determinant (GPpref.py:131) halved again in ``log_marginal`` (GPpref.py:93).  The opt-in
+``newton=True`` constructor flag gives the accumulated gradient (true Newton steps).
+"""
+import numpy as np
+
+from . import _lib
+
+_sqrt_2pi = np.sqrt(2 * np.pi)
+
+
+def _handle():
+    return _lib.default_handle()
+
+
+def std_norm_pdf(x):
+    """GPpref.py:7-10 (scalar helper kept on the host; the device kernels have their own)."""
+    x = np.clip(x, -1e150, 1e150)
+    return np.exp(-(x ** 2) / 2) / _sqrt_2pi
+
+
+class RBF(object):
+    """Stand-in for ``GPy.kern.RBF(input_dim, ARD=True)`` (GPpref.py:109): holds ``lengthscale`` and
+    ``variance`` and evaluates ``K`` on the device (r^2 clipped at 0, exact zero diagonal)."""
+
+    def __init__(self, input_dim, ARD=True):
+        self.input_dim = input_dim
+        self.ARD = ARD
+        self.lengthscale = np.ones(input_dim)
+        self.variance = 1.0
+
+    def khyp(self):
+        ls = np.broadcast_to(np.asarray(self.lengthscale, dtype=float).reshape(-1), (self.input_dim,))
+        return np.concatenate([ls, [float(self.variance)]])
+
+    def K(self, X):
+        h = _handle()
+        h.set_train(X)
+        return h.kxx(np.concatenate([self.khyp(), [0.0]]), flags=1)
+
+
+class PrefProbit(object):
+    """GPpref.py:46-94."""
+
+    def __init__(self, sigma=1.0):
+        self.set_sigma(sigma)
+        self.log2pi = np.log(2.0 * np.pi)
+
+    def set_sigma(self, sigma):
+        self.sigma = sigma                                         # GPpref.py:52
+        self._isqrt2sig = 1.0 / (self.sigma * np.sqrt(2.0))        # GPpref.py:53
+        self._i2var = self._isqrt2sig ** 2                         # GPpref.py:54
+
+    def z_k(self, uvi, f, y):
+        """GPpref.py:56-58 (an index gather; stays on the host for callers that want z itself)."""
+        zc = self._isqrt2sig * (f[uvi[:, 1]] - f[uvi[:, 0]])
+        return y * zc
+
+    def I_k(self, x, uv):
+        """GPpref.py:60-66 (unused by the reference as well)."""
+        if x == uv[0]:
+            return -1
+        elif x == uv[1]:
+            return 1
+        else:
+            return 0
+
+    def derivatives(self, uvi, y, f, accumulate=False):
+        """GPpref.py:68-88: dense W (n,n) and the gradient (n,1), computed on the device."""
+        f = np.asarray(f, dtype=float)
+        W, g = _handle().pref_derivatives(uvi, np.asarray(y, dtype=float), f.reshape(-1), sigma=self.sigma,
+                                          grad_mode=1 if accumulate else 0)
+        return W, g.reshape(-1, 1)
+
+    def log_marginal(self, uvi, y, f, iK, logdetK):
+        """GPpref.py:90-94 for caller-supplied iK / logdetK (small host expression; inside
+        ``calc_laplace`` the same quantity is reduced on the device)."""
+        from math import erfc, log, sqrt
+        z = np.asarray(self.z_k(uvi, f, y), dtype=float).reshape(-1)
+        s = sum(log(0.5 * erfc(-zi / sqrt(2.0))) for zi in z)
+        fv = np.asarray(f, dtype=float).reshape(-1, 1)
+        psi = s - 0.5 * (fv.T @ iK @ fv) - 0.5 * logdetK - iK.shape[0] / 2.0 * self.log2pi
+        return np.asarray(psi).flat[0]
+
+
+class PreferenceGaussianProcess(object):
+    """GPpref.py:96-161."""
+
+    def __init__(self, x_train, uvi_train, y_train, likelihood=PrefProbit, delta_f=1e-6, newton=False,
+                 max_iter=10000):
+        # log_hyp layout: [length_0, ..., length_d, sigma_f, sigma_probit]  (GPpref.py:99)
+        self._xdim = x_train.shape[1]
+        self._nx = x_train.shape[0]
+        self.x_train = x_train
+        self.y_train = y_train
+        self.uvi_train = uvi_train
+        self.delta_f = delta_f
+        self.likelihood = likelihood()
+        self.kern = RBF(self._xdim, ARD=True)
+        self.newton = newton            # not in the reference: accumulate the gradient (true Newton)
+        self.max_iter = max_iter        # the reference loops without a cap (GPpref.py:140)
+        self.trace = None               # per-iteration (f_error, lml): what the reference prints (GPpref.py:154)
+        self.n_iter = 0
+        self.jitter = None
+
+    def calc_laplace(self, loghyp, f=None):
+        """GPpref.py:112-157: returns (f (n,1), lml)."""
+        self.kern.lengthscale = np.exp(loghyp[0:self._xdim])              # GPpref.py:113
+        self.kern.variance = (np.exp(loghyp[self._xdim])) ** 2            # GPpref.py:114
+        self.likelihood.set_sigma = np.exp(loghyp[-1])                    # GPpref.py:115 (sic: sigma unchanged)
+        h = _handle()
+        h.set_train(self.x_train)
+        f0 = None if f is None else np.asarray(f, dtype=float).reshape(-1)
+        fv, lml, iters, trace, jitter = h.pref_laplace(
+            self.uvi_train, np.asarray(self.y_train, dtype=float).reshape(-1), self.kern.khyp(),
+            sigma=self.likelihood.sigma, delta_f=self.delta_f, max_iter=self.max_iter,
+            grad_mode=1 if self.newton else 0, f0=f0)
+        self.trace, self.n_iter, self.jitter = trace, iters, jitter
+        return fv.reshape(-1, 1), lml
+
+    def calc_nlml(self, loghyp):
+        """GPpref.py:159-161."""
+        f, lml = self.calc_laplace(loghyp)
+        return -lml

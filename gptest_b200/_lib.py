@@ -262,3 +262,71 @@ def default_handle(device=None):
     if h is None:
         h = _default[device] = Handle(device)
     return h
+
+
+# ---- Laplace paths (attached to Handle below to keep the class body readable) -----------------
+def _pref_laplace(self, uvi, y, khyp, sigma=1.0, delta_f=1e-6, max_iter=1000, grad_mode=0, f0=None):
+    """PreferenceGaussianProcess.calc_laplace on the device: returns (f (n,), lml, iters, trace, jitter)."""
+    uvi = np.ascontiguousarray(uvi, dtype=np.int64).reshape(-1, 2)
+    y = as_f64(y).reshape(-1)
+    khyp = as_f64(khyp)
+    P = uvi.shape[0]
+    assert y.shape[0] == P
+    f = np.zeros(self.n) if f0 is None else as_f64(f0).reshape(-1).copy()
+    lml = C.c_double()
+    iters = C.c_int32()
+    info = C.c_int32()
+    jit = C.c_double()
+    trace = np.zeros((int(max_iter), 2))
+    rc = self.lib.gpb_pref_laplace(self.h, uvi.ctypes.data_as(c_lp), _dp(y), P, _dp(khyp), float(sigma), float(delta_f),
+                                   int(max_iter), int(grad_mode), 0 if f0 is None else 1, _dp(f), C.byref(lml),
+                                   C.byref(iters), _dp(trace), C.byref(jit), C.byref(info))
+    if rc != 0 and info.value > 0:
+        raise np.linalg.LinAlgError(self.lib.gpb_last_error(self.h).decode())
+    self.check(rc)
+    return f, lml.value, iters.value, trace[:iters.value].copy(), jit.value
+
+
+def _pref_derivatives(self, uvi, y, f, sigma=1.0, grad_mode=0):
+    uvi = np.ascontiguousarray(uvi, dtype=np.int64).reshape(-1, 2)
+    y = as_f64(y).reshape(-1)
+    f = as_f64(f).reshape(-1)
+    n = f.shape[0]
+    W = np.empty((n, n))
+    g = np.empty(n)
+    self.check(self.lib.gpb_pref_derivatives(self.h, uvi.ctypes.data_as(c_lp), _dp(y), uvi.shape[0], n, _dp(f),
+                                             float(sigma), int(grad_mode), _dp(W), _dp(g)))
+    return W, g
+
+
+def _gpc_laplace(self, y, khyp, link=0, delta_f=1e-6, max_iter=100, f0=None):
+    y = as_f64(y).reshape(-1)
+    khyp = as_f64(khyp)
+    f = np.zeros(self.n) if f0 is None else as_f64(f0).reshape(-1).copy()
+    lml = C.c_double()
+    iters = C.c_int32()
+    info = C.c_int32()
+    jit = C.c_double()
+    trace = np.zeros((int(max_iter), 2))
+    rc = self.lib.gpb_gpc_laplace(self.h, _dp(y), _dp(khyp), int(link), float(delta_f), int(max_iter),
+                                  0 if f0 is None else 1, _dp(f), C.byref(lml), C.byref(iters), _dp(trace),
+                                  C.byref(jit), C.byref(info))
+    if rc != 0 and info.value > 0:
+        raise np.linalg.LinAlgError(self.lib.gpb_last_error(self.h).decode())
+    self.check(rc)
+    return f, lml.value, iters.value, trace[:iters.value].copy(), jit.value
+
+
+def _gpc_predict(self, Z):
+    Z = as_f64(Z)
+    Z = Z.reshape(len(Z), -1)
+    m = Z.shape[0]
+    mu, var, p = np.empty(m), np.empty(m), np.empty(m)
+    self.check(self.lib.gpb_gpc_predict(self.h, _dp(Z), m, _dp(mu), _dp(var), _dp(p)))
+    return mu, var, p
+
+
+Handle.pref_laplace = _pref_laplace
+Handle.pref_derivatives = _pref_derivatives
+Handle.gpc_laplace = _gpc_laplace
+Handle.gpc_predict = _gpc_predict

@@ -78,6 +78,8 @@ struct gpb_handle {
 
   // Laplace state kept for prediction
   int64_t lap_n = 0;
+  int lap_link = 0;
+  std::vector<double> lap_khyp;
 
   cudaEvent_t next_event();
   double* pinned(size_t bytes);

@@ -1,25 +1,762 @@
-// laplace.cu - Laplace / Newton mode finding for GPc and GPpref (stage under construction).
+// laplace.cu - Laplace / Newton mode finding on the device.
+//
+//  * preference GP (PreferenceGaussianProcess.calc_laplace, GPpref.py:112-157, PrefProbit
+//    GPpref.py:46-94) including the reference's quirks (see gpb200.h);
+//  * binary classification (GPc.py intent; Rasmussen & Williams Alg. 3.1 / 3.2).
+//
+// Per Newton iteration the reference inverts a dense n x n matrix on the host
+// (np.linalg.inv, GPpref.py:143) and builds W with a Python loop over the pairs
+// (GPpref.py:82-87).  Here one iteration is: a fused per-pair kernel (z, Phi, N, gradient and
+// Hessian weights), a per-item kernel that assembles G = K^-1 + W and the right-hand side from a
+// CSR view of the comparison graph (deterministic, same per-cell summation order as the
+// reference's loop), the blocked DMMA Cholesky of G with the right-hand side riding along as an
+// appended row, a blocked backward substitution, and one reduction kernel for the objective and
+// max|f_new - f|.  The host only reads back 16 bytes per iteration to decide on convergence.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
 #include "../../include/gpb200.h"
 #include "gpb_context.cuh"
 
+using namespace gpb;
+
+namespace {
+
+constexpr double LOG_2PI = 1.8378770664093453;
+constexpr double INV_SQRT_2PI = 0.3989422804014327;
+constexpr double SQRT_2_OVER_PI = 0.7978845608028654;
+constexpr double INV_SQRT_2 = 0.7071067811865476;
+
+// ---------------------------------------------------------------------------------------
+// generic helpers
+// ---------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ double cta_sum(double v, double* sh) {
+  sh[threadIdx.x] = v;
+  __syncthreads();
+#pragma unroll
+  for (int w = NT / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+template <int NT>
+__device__ __forceinline__ double cta_max(double v, double* sh) {
+  sh[threadIdx.x] = v;
+  __syncthreads();
+#pragma unroll
+  for (int w = NT / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + w]);
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(512) sum_log_kernel(const double* __restrict__ v, int64_t n, double* __restrict__ out) {
+  __shared__ double sh[512];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 512) s += log(v[i]);
+  const double r = cta_sum<512>(s, sh);
+  if (threadIdx.x == 0) out[0] = r;
+}
+
+// full symmetric copy of a matrix whose lower 64-tiles (and full diagonal tiles) are valid
+__global__ void __launch_bounds__(256) mirror_lower_kernel(const double* __restrict__ src, int64_t ld_s,
+                                                           double* __restrict__ dst, int64_t ld_d, int64_t nt64) {
+  __shared__ double tt[64][65];
+  const int64_t ti = blockIdx.x / nt64, tj = blockIdx.x % nt64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  if (ti >= tj) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int64_t r = ti * 64 + ty + 16 * a, cc = tj * 64 + tx + 16 * c;
+        dst[r * ld_d + cc] = src[r * ld_s + cc];
+      }
+  } else {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        tt[ty + 16 * a][tx + 16 * c] = src[(tj * 64 + ty + 16 * a) * ld_s + ti * 64 + tx + 16 * c];
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        dst[(ti * 64 + ty + 16 * a) * ld_d + tj * 64 + tx + 16 * c] = tt[tx + 16 * c][ty + 16 * a];
+  }
+}
+
+// lower triangle (row by row) of dst <- rs[r] * src * rs[c] + (r == c ? dadd : 0); rs == nullptr: plain copy
+__global__ void __launch_bounds__(256) scale_copy_lower_kernel(const double* __restrict__ src, int64_t ld_s,
+                                                               double* __restrict__ dst, int64_t ld_d,
+                                                               const double* __restrict__ rs, double dadd) {
+  const int64_t r = blockIdx.x;
+  const double sr = rs ? rs[r] : 1.0;
+  for (int64_t c = threadIdx.x; c <= r; c += 256) {
+    double v = src[r * ld_s + c];
+    if (rs) v = sr * v * rs[c];
+    if (c == r) v += dadd;
+    dst[r * ld_d + c] = v;
+  }
+}
+
+// One step of the blocked backward substitution  L^T x = r  with the inverted diagonal tiles:
+//   x_k = W_k^T r_k ;  r_c -= sum_{rows of tile k} L[row][c] x_k[row]   for every column c left of tile k.
+__global__ void __launch_bounds__(256) trsv_lt_step_kernel(const double* __restrict__ L, int64_t ld,
+                                                           const double* __restrict__ Dinv, int k,
+                                                           double* __restrict__ r, double* __restrict__ x) {
+  __shared__ double rk[TILE];
+  __shared__ double xk[TILE];
+  const int t = threadIdx.x;
+  if (t < TILE) rk[t] = r[k * TILE + t];
+  __syncthreads();
+  if (t < TILE) {
+    const double* W = Dinv + static_cast<int64_t>(k) * TILE * TILE;
+    double s = 0.0;
+    for (int row = t; row < TILE; ++row) s = fma(W[row * TILE + t], rk[row], s);   // W lower: rows >= column
+    xk[t] = s;
+    if (blockIdx.x == 0) x[k * TILE + t] = s;
+  }
+  __syncthreads();
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * 256 + t;
+  if (c < static_cast<int64_t>(k) * TILE) {
+    const double* Lk = L + static_cast<int64_t>(k) * TILE * ld + c;
+    double s = 0.0;
+#pragma unroll 8
+    for (int row = 0; row < TILE; ++row) s = fma(Lk[row * ld], xk[row], s);
+    r[c] -= s;
+  }
+}
+
+void trsv_lt(gpb_handle* h, const FactorMat& m, double* r, double* x) {
+  const int nt = static_cast<int>(m.n_pad / TILE);
+  for (int k = nt - 1; k >= 0; --k) {
+    const int blocks = k == 0 ? 1 : (k * TILE + 255) / 256;
+    trsv_lt_step_kernel<<<blocks, 256, 0, h->s0>>>(m.A, m.ld, m.Dinv, k, r, x);
+    GPB_CUDA(cudaGetLastError());
+    ++h->launches;
+  }
+}
+
+// FactorMat over h->A with the (2 np + 128)-row layout shared with grad.cu
+FactorMat laplace_mat(gpb_handle* h, int64_t rows_total) {
+  const int64_t np = h->n_pad;
+  const int64_t rows_alloc = 2 * np + TILE;
+  FactorMat m;
+  m.ld = np; m.n_pad = np; m.rows_total = rows_total; m.batch = 1;
+  m.batch_stride = rows_alloc * np;
+  h->A.ensure(static_cast<size_t>(m.batch_stride) * 8);
+  m.A = h->A.as<double>();
+  m.dinv_bs = np * TILE;
+  h->Dinv.ensure(static_cast<size_t>(m.dinv_bs) * 8);
+  m.Dinv = h->Dinv.as<double>();
+  m.diag_bs = np;
+  h->diag.ensure(static_cast<size_t>(np) * 8);
+  m.diag = h->diag.as<double>();
+  h->info.ensure(64);
+  m.info = h->info.as<int>();
+  finalize_factor_mat(m);
+  make_tensor_map(&m.mapA, m.A, np, rows_alloc, 1, np, m.batch_stride);
+  return m;
+}
+
+// K (+ jitter on the diagonal) from the training inputs: lower tiles into dst (mode 1) or full (mode 0)
+void build_kernel_matrix(gpb_handle* h, const double* ell_dev, const double* hyp2_dev, double* dst, int64_t ld, int mode) {
+  const int64_t np = h->n_pad;
+  h->XsT.ensure(static_cast<size_t>(h->d) * np * 8);
+  h->sq.ensure(static_cast<size_t>(np) * 8);
+  launch_se_prep(h->X.as<double>(), h->n, h->d, ell_dev, h->XsT.as<double>(), np, h->sq.as<double>(), 1, 0, 0, 0, h->s0);
+  SeArgs a{};
+  a.rT = a.cT = h->XsT.as<double>(); a.r_ld = a.c_ld = np;
+  a.r_sq = a.c_sq = h->sq.as<double>();
+  a.n_rows_valid = a.n_cols_valid = h->n;
+  a.d = h->d; a.out = dst; a.ld = ld; a.rows_pad = a.cols_pad = np;
+  a.hyp_dev = hyp2_dev; a.mode = mode; a.clip = 1;        // GPy RBF semantics (GPpref.py:122)
+  launch_se_build(a, 1, h->s0);
+  h->launches += 2;
+}
+
+int read_info(gpb_handle* h, const FactorMat& m) {
+  double* host = h->pinned(64);
+  GPB_CUDA(cudaMemcpyAsync(host, m.info, 4, cudaMemcpyDeviceToHost, h->s0));
+  GPB_CUDA(cudaStreamSynchronize(h->s0));
+  return *reinterpret_cast<int*>(host);
+}
+
+// upload [ell..., variance, jitter]; returns device pointers (ell, hyp2)
+void upload_kernel_params(gpb_handle* h, const double* khyp, double jitter, const double** ell, const double** hyp2) {
+  const int d = h->d;
+  double* host = h->pinned((d + 2) * 8);
+  for (int k = 0; k < d; ++k) host[k] = khyp[k];
+  host[d] = khyp[d];
+  host[d + 1] = jitter;
+  h->params.ensure((d + 2) * 8);
+  GPB_CUDA(cudaMemcpyAsync(h->params.p, host, (d + 2) * 8, cudaMemcpyHostToDevice, h->s0));
+  GPB_CUDA(cudaStreamSynchronize(h->s0));
+  *ell = h->params.as<double>();
+  *hyp2 = h->params.as<double>() + d;
+}
+
+// ---------------------------------------------------------------------------------------
+// preference likelihood (PrefProbit, GPpref.py:46-94)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double pref_hazard(double z) {
+  // N(z)/Phi(z) as the reference forms it (GPpref.py:71-72,76); where Phi underflows (z < -37,
+  // the reference produces 0/0 = nan) the erfcx form keeps the iteration finite.
+  const double phi = normcdf(z);
+  if (phi > 1e-300) return exp(-0.5 * z * z) * INV_SQRT_2PI / phi;
+  return SQRT_2_OVER_PI / erfcx(-z * INV_SQRT_2);
+}
+
+// per pair: d_k = y isqrt2sig N/Phi (GPpref.py:76), w_k = i2var (z N/Phi + (N/Phi)^2) = -inner (GPpref.py:80)
+__global__ void pref_pair_kernel(const int64_t* __restrict__ uvi, const double* __restrict__ y, int64_t P,
+                                 const double* __restrict__ f, double isqrt2sig, double i2var,
+                                 double* __restrict__ dk, double* __restrict__ wk) {
+  const int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (k >= P) return;
+  const int64_t u = uvi[2 * k], v = uvi[2 * k + 1];
+  const double z = y[k] * (isqrt2sig * (f[v] - f[u]));       // GPpref.py:56-58
+  const double r = pref_hazard(z);
+  dk[k] = y[k] * isqrt2sig * r;
+  wk[k] = i2var * (z * r + r * r);
+}
+
+struct PrefGraphDev {
+  const int64_t* row_ptr;      // n + 1
+  const int32_t* other;        // per row: the other item of each incident pair, sorted by (other, pair)
+  const int32_t* pair_by_other;
+  const int32_t* is_u;         // 1: the row item is u (column 0) of that pair
+  const int32_t* pair_sorted;  // per row: incident pairs in ascending pair order (diagonal cell)
+  const int64_t* ku;           // last pair with u == i, or -1 (GPpref.py:77 last write wins)
+  const int64_t* kv;           // last pair with v == i, or -1 (GPpref.py:78)
+};
+
+// per item i: gradient g_i, row i of G = K^-1 + W (lower part), b_i = (W f)_i + g_i.
+// Every cell of W is accumulated in pair order like the reference's loop (GPpref.py:82-87) and only
+// then added to K^-1 (GPpref.py:142).
+__global__ void pref_row_kernel(int64_t n, const PrefGraphDev gr, const double* __restrict__ dk,
+                                const double* __restrict__ wk, const double* __restrict__ f, int grad_mode,
+                                double* __restrict__ G, int64_t ld, double* __restrict__ b,
+                                double* __restrict__ g_out, double* __restrict__ Wdense) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  double g = 0.0;
+  if (grad_mode == 0) {
+    if (gr.ku[i] >= 0) g = 0.0 - dk[gr.ku[i]];     // column-0 pass: g[u] = 0 + (-d)
+    if (gr.kv[i] >= 0) g = g + dk[gr.kv[i]];       // column-1 pass adds to whatever pass 0 left
+  }
+  const int64_t e0 = gr.row_ptr[i], e1 = gr.row_ptr[i + 1];
+  double wf = 0.0;
+  int64_t e = e0;
+  while (e < e1) {
+    const int32_t j = gr.other[e];
+    double wij = 0.0;
+    while (e < e1 && gr.other[e] == j) {
+      wij -= wk[gr.pair_by_other[e]];              // W[xi, yi] -= -ddpy_df (GPpref.py:86-87)
+      ++e;
+    }
+    wf = fma(wij, f[j], wf);
+    if (G && j < i) G[i * ld + j] += wij;
+    if (Wdense) Wdense[i * n + j] = wij;
+  }
+  double wii = 0.0;
+  for (int64_t q = e0; q < e1; ++q) {
+    const int32_t k = gr.pair_sorted[q];
+    wii += wk[k];                                  // W[xi, xi] -= ddpy_df (GPpref.py:84-85)
+  }
+  if (grad_mode == 1) {
+    for (int64_t q = e0; q < e1; ++q) g += gr.is_u[q] ? -dk[gr.pair_by_other[q]] : dk[gr.pair_by_other[q]];
+  }
+  wf = fma(wii, f[i], wf);
+  if (G) G[i * ld + i] += wii;
+  if (Wdense) Wdense[i * n + i] = wii;
+  if (b) b[i] = wf + g;
+  if (g_out) g_out[i] = g;
+}
+
+// lml = sum log Phi(z(f_new)) - 0.5 f_new' iK f_new - 0.5 logdetK - n/2 log(2 pi)   (GPpref.py:90-94)
+// f_error = max |f_new - f| (GPpref.py:151-152); then f <- f_new (GPpref.py:155)
+__global__ void __launch_bounds__(1024) pref_finish_kernel(const int64_t* __restrict__ uvi, const double* __restrict__ y,
+                                                           int64_t P, int64_t n, double isqrt2sig,
+                                                           const double* __restrict__ f_new, double* __restrict__ f,
+                                                           const double* __restrict__ t, const double* __restrict__ logdet,
+                                                           double* __restrict__ out2) {
+  __shared__ double sh[1024];
+  double s = 0.0;
+  for (int64_t k = threadIdx.x; k < P; k += 1024) {
+    const double z = y[k] * (isqrt2sig * (f_new[uvi[2 * k + 1]] - f_new[uvi[2 * k]]));
+    s += log(normcdf(z));
+  }
+  const double slog = cta_sum<1024>(s, sh);
+  double q = 0.0, mx = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) {
+    q = fma(f_new[i], t[i], q);
+    mx = fmax(mx, fabs(f_new[i] - f[i]));
+    f[i] = f_new[i];
+  }
+  const double qs = cta_sum<1024>(q, sh);
+  const double m = cta_max<1024>(mx, sh);
+  if (threadIdx.x == 0) {
+    out2[0] = m;
+    out2[1] = slog - 0.5 * qs - 0.5 * logdet[0] - 0.5 * static_cast<double>(n) * LOG_2PI;
+  }
+}
+
+struct PrefGraphHost {
+  std::vector<int64_t> row_ptr, ku, kv;
+  std::vector<int32_t> other, pair_by_other, is_u, pair_sorted;
+};
+
+PrefGraphHost build_pref_graph(const int64_t* uvi, int64_t P, int64_t n) {
+  PrefGraphHost g;
+  g.row_ptr.assign(n + 1, 0);
+  g.ku.assign(n, -1);
+  g.kv.assign(n, -1);
+  for (int64_t k = 0; k < P; ++k) {
+    const int64_t u = uvi[2 * k], v = uvi[2 * k + 1];
+    if (u < 0 || u >= n || v < 0 || v >= n) throw Error{"uvi index out of range"};
+    g.ku[u] = k;                       // later pairs overwrite earlier ones
+    g.kv[v] = k;
+    if (u != v) { ++g.row_ptr[u + 1]; ++g.row_ptr[v + 1]; }     // u == v contributes exactly zero to W
+  }
+  for (int64_t i = 0; i < n; ++i) g.row_ptr[i + 1] += g.row_ptr[i];
+  const int64_t nnz = g.row_ptr[n];
+  g.other.resize(nnz); g.pair_by_other.resize(nnz); g.is_u.resize(nnz); g.pair_sorted.resize(nnz);
+  std::vector<int64_t> fill(g.row_ptr.begin(), g.row_ptr.end() - 1);
+  struct Ent { int32_t other, pair, is_u; };
+  std::vector<Ent> ent(nnz);
+  for (int64_t k = 0; k < P; ++k) {
+    const int64_t u = uvi[2 * k], v = uvi[2 * k + 1];
+    if (u == v) continue;
+    ent[fill[u]++] = Ent{static_cast<int32_t>(v), static_cast<int32_t>(k), 1};
+    ent[fill[v]++] = Ent{static_cast<int32_t>(u), static_cast<int32_t>(k), 0};
+  }
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t e0 = g.row_ptr[i], e1 = g.row_ptr[i + 1];
+    for (int64_t e = e0; e < e1; ++e) g.pair_sorted[e] = ent[e].pair;      // filled in ascending pair order
+    std::stable_sort(ent.begin() + e0, ent.begin() + e1, [](const Ent& a, const Ent& b) { return a.other < b.other; });
+    for (int64_t e = e0; e < e1; ++e) {
+      g.other[e] = ent[e].other;
+      g.pair_by_other[e] = ent[e].pair;
+      g.is_u[e] = ent[e].is_u;
+    }
+  }
+  return g;
+}
+
+// device copy of the graph + pairs, carved out of one buffer
+struct PrefDev {
+  PrefGraphDev gr;
+  const int64_t* uvi;
+  const double* y;
+  double *dk, *wk;
+};
+
+PrefDev upload_pref(gpb_handle* h, const PrefGraphHost& g, const int64_t* uvi, const double* y, int64_t P, int64_t n) {
+  const int64_t nnz = g.row_ptr[n];
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+  const size_t o_rp = take((n + 1) * 8), o_ku = take(n * 8), o_kv = take(n * 8), o_uvi = take(P * 16),
+               o_y = take(P * 8), o_dk = take(P * 8), o_wk = take(P * 8), o_ot = take(nnz * 4 + 4),
+               o_pb = take(nnz * 4 + 4), o_iu = take(nnz * 4 + 4), o_ps = take(nnz * 4 + 4);
+  h->aux1.ensure(off);
+  char* base = h->aux1.as<char>();
+  auto up = [&](size_t o, const void* src, size_t bytes) {
+    if (bytes) GPB_CUDA(cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, h->s0));
+  };
+  up(o_rp, g.row_ptr.data(), (n + 1) * 8); up(o_ku, g.ku.data(), n * 8); up(o_kv, g.kv.data(), n * 8);
+  up(o_uvi, uvi, P * 16); up(o_y, y, P * 8);
+  up(o_ot, g.other.data(), nnz * 4); up(o_pb, g.pair_by_other.data(), nnz * 4);
+  up(o_iu, g.is_u.data(), nnz * 4); up(o_ps, g.pair_sorted.data(), nnz * 4);
+  GPB_CUDA(cudaStreamSynchronize(h->s0));
+  PrefDev d;
+  d.gr.row_ptr = reinterpret_cast<const int64_t*>(base + o_rp);
+  d.gr.ku = reinterpret_cast<const int64_t*>(base + o_ku);
+  d.gr.kv = reinterpret_cast<const int64_t*>(base + o_kv);
+  d.gr.other = reinterpret_cast<const int32_t*>(base + o_ot);
+  d.gr.pair_by_other = reinterpret_cast<const int32_t*>(base + o_pb);
+  d.gr.is_u = reinterpret_cast<const int32_t*>(base + o_iu);
+  d.gr.pair_sorted = reinterpret_cast<const int32_t*>(base + o_ps);
+  d.uvi = reinterpret_cast<const int64_t*>(base + o_uvi);
+  d.y = reinterpret_cast<const double*>(base + o_y);
+  d.dk = reinterpret_cast<double*>(base + o_dk);
+  d.wk = reinterpret_cast<double*>(base + o_wk);
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------
+// classification likelihood (GPc.py:4-21; R&W eq. 3.15 / 3.16)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void gpc_terms(int link, double y, double f, double& lp, double& g, double& W) {
+  if (link == 0) {                                  // probit: log Phi(y f)  (GPc.py:5-6)
+    const double x = y * f;
+    const double ex = erfcx(-x * INV_SQRT_2);       // Phi(x) = 0.5 erfcx(-x/sqrt2) exp(-x^2/2)
+    const double r = SQRT_2_OVER_PI / ex;           // N(f)/Phi(yf), finite for every x
+    lp = (x < 0.0) ? log(0.5 * ex) - 0.5 * x * x : log(normcdf(x));
+    g = y * r;
+    W = r * r + x * r;
+  } else {                                          // logistic (GPc.py:13-14)
+    const double x = y * f;
+    lp = (x > 0.0) ? -log1p(exp(-x)) : x - log1p(exp(x));
+    const double pi = 1.0 / (1.0 + exp(-f));
+    g = 0.5 * (y + 1.0) - pi;
+    W = pi * (1.0 - pi);
+  }
+}
+
+// b = W f + g ; sW = sqrt(W) ; pads get W = 0
+__global__ void gpc_terms_kernel(int link, const double* __restrict__ y, const double* __restrict__ f, int64_t n,
+                                 int64_t n_pad, double* __restrict__ sW, double* __restrict__ b, double* __restrict__ g_out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n_pad) return;
+  if (i >= n) { sW[i] = 0.0; b[i] = 0.0; if (g_out) g_out[i] = 0.0; return; }
+  double lp, g, W;
+  gpc_terms(link, y[i], f[i], lp, g, W);
+  sW[i] = sqrt(W);
+  b[i] = fma(W, f[i], g);
+  if (g_out) g_out[i] = g;
+}
+__global__ void vec_mul_kernel(double* __restrict__ dst, const double* __restrict__ a, const double* __restrict__ b, int64_t n) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) dst[i] = a[i] * b[i];
+}
+// a = b - sW * t
+__global__ void gpc_a_kernel(double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ sW,
+                             const double* __restrict__ t, int64_t n) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) a[i] = b[i] - sW[i] * t[i];
+}
+// out2 = (max|f_new - f|, -0.5 a'f_new + sum log p(y|f_new)); f <- f_new
+__global__ void __launch_bounds__(1024) gpc_finish_kernel(int link, const double* __restrict__ y, int64_t n,
+                                                          const double* __restrict__ a, const double* __restrict__ f_new,
+                                                          double* __restrict__ f, double* __restrict__ out2) {
+  __shared__ double sh[1024];
+  double q = 0.0, mx = 0.0, sl = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) {
+    double lp, g, W;
+    gpc_terms(link, y[i], f_new[i], lp, g, W);
+    sl += lp;
+    q = fma(a[i], f_new[i], q);
+    mx = fmax(mx, fabs(f_new[i] - f[i]));
+    f[i] = f_new[i];
+  }
+  const double qs = cta_sum<1024>(q, sh);
+  const double ls = cta_sum<1024>(sl, sh);
+  const double m = cta_max<1024>(mx, sh);
+  if (threadIdx.x == 0) { out2[0] = m; out2[1] = -0.5 * qs + ls; }
+}
+// rows[i][j] *= s[j]
+__global__ void scale_cols_kernel(double* __restrict__ rows, int64_t ld, int64_t ncols, const double* __restrict__ s) {
+  double* r = rows + blockIdx.x * ld;
+  for (int64_t j = threadIdx.x; j < ncols; j += blockDim.x) r[j] *= s[j];
+}
+// var_i = sf2 - |row_i|^2 ; prob_i from (mu_i, var_i)
+__global__ void __launch_bounds__(256) gpc_predict_finish_kernel(const double* __restrict__ rows, int64_t ld, int64_t ncols,
+                                                                 double sf2, int link, const double* __restrict__ mu,
+                                                                 double* __restrict__ var, double* __restrict__ prob) {
+  __shared__ double sh[256];
+  const double* r = rows + blockIdx.x * ld;
+  double s = 0.0;
+  for (int64_t j = threadIdx.x; j < ncols; j += 256) s = fma(r[j], r[j], s);
+  const double ss = cta_sum<256>(s, sh);
+  if (threadIdx.x == 0) {
+    const double v = sf2 - ss;
+    var[blockIdx.x] = v;
+    const double m = mu[blockIdx.x];
+    prob[blockIdx.x] = (link == 0) ? normcdf(m / sqrt(1.0 + v))                                   // R&W eq. 3.82
+                                   : 1.0 / (1.0 + exp(-m / sqrt(1.0 + 0.39269908169872414 * v)));   // MacKay, pi/8
+  }
+}
+
+}  // namespace
+
+#define LAP_BEGIN                                      \
+  if (!h) return -1;                                   \
+  try {                                                \
+    GPB_CUDA(cudaSetDevice(h->device));
+#define LAP_END                                        \
+  }                                                    \
+  catch (const gpb::Error& e) {                        \
+    h->err = e.msg;                                    \
+    return -2;                                         \
+  }                                                    \
+  catch (const std::exception& e) {                    \
+    h->err = e.what();                                 \
+    return -3;                                         \
+  }                                                    \
+  return 0;
+
 extern "C" {
-int gpb_gpc_laplace(gpb_handle* h, const double*, const double*, int32_t, double, int32_t, int32_t, double*,
-                    double*, int32_t*, double*, double*, int32_t*) {
-  if (h) h->err = "gpc_laplace not built yet";
-  return -4;
+
+int gpb_pref_derivatives(gpb_handle* h, const int64_t* uvi, const double* y, int64_t P, int64_t n, const double* f,
+                         double sigma, int32_t grad_mode, double* W_out, double* g_out) {
+  LAP_BEGIN
+  GPB_REQUIRE(uvi && y && f && P > 0 && n > 0 && W_out && g_out, "null argument");
+  PrefGraphHost g = build_pref_graph(uvi, P, n);
+  PrefDev pd = upload_pref(h, g, uvi, y, P, n);
+  h->aux0.ensure(static_cast<size_t>(n) * 16);
+  h->aux2.ensure(static_cast<size_t>(n) * n * 8);
+  double* fd = h->aux0.as<double>();
+  double* gd = fd + n;
+  GPB_CUDA(cudaMemcpyAsync(fd, f, n * 8, cudaMemcpyHostToDevice, h->s0));
+  GPB_CUDA(cudaMemsetAsync(h->aux2.p, 0, static_cast<size_t>(n) * n * 8, h->s0));
+  const double isq = 1.0 / (sigma * std::sqrt(2.0)), i2v = isq * isq;      // GPpref.py:53-54
+  pref_pair_kernel<<<static_cast<unsigned>((P + 255) / 256), 256, 0, h->s0>>>(pd.uvi, pd.y, P, fd, isq, i2v, pd.dk, pd.wk);
+  pref_row_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, h->s0>>>(n, pd.gr, pd.dk, pd.wk, fd, grad_mode,
+                                                                            nullptr, 0, nullptr, gd, h->aux2.as<double>());
+  GPB_CUDA(cudaGetLastError());
+  h->launches += 2;
+  GPB_CUDA(cudaMemcpyAsync(W_out, h->aux2.p, static_cast<size_t>(n) * n * 8, cudaMemcpyDeviceToHost, h->s0));
+  GPB_CUDA(cudaMemcpyAsync(g_out, gd, n * 8, cudaMemcpyDeviceToHost, h->s0));
+  GPB_CUDA(cudaStreamSynchronize(h->s0));
+  LAP_END
 }
-int gpb_gpc_predict(gpb_handle* h, const double*, int64_t, double*, double*, double*) {
-  if (h) h->err = "gpc_predict not built yet";
-  return -4;
+
+int gpb_pref_laplace(gpb_handle* h, const int64_t* uvi, const double* y, int64_t P, const double* khyp, double sigma,
+                     double delta_f, int32_t max_iter, int32_t grad_mode, int32_t use_f0, double* f_inout, double* lml,
+                     int32_t* iters, double* trace, double* jitter, int32_t* info) {
+  LAP_BEGIN
+  GPB_REQUIRE(h->n > 0, "no training inputs: call gpb_set_train first");
+  GPB_REQUIRE(uvi && y && khyp && f_inout && lml && iters && P > 0 && max_iter > 0, "null argument");
+  const int64_t n = h->n, np = h->n_pad;
+  if (info) *info = 0;
+  PrefGraphHost graph = build_pref_graph(uvi, P, n);
+  PrefDev pd = upload_pref(h, graph, uvi, y, P, n);
+  GPB_CUDA(cudaEventRecord(h->tev[0], h->s0));
+
+  // ---- K + eps I, its factor, log-determinant and explicit inverse (GPpref.py:121-135) ----
+  double eps = 1e-6;                                                       // GPpref.py:123
+  FactorMat m = laplace_mat(h, np);
+  const double *ell, *hyp2;
+  for (;;) {
+    upload_kernel_params(h, khyp, eps, &ell, &hyp2);
+    GPB_CUDA(cudaMemsetAsync(m.info, 0, 4, h->s0));
+    build_kernel_matrix(h, ell, hyp2, m.A, m.ld, 1);
+    m.rows_total = np;
+    chol_sweep(h, m, true);
+    if (read_info(h, m) == 0) break;
+    eps *= 10.0;                                                           // GPpref.py:134
+    if (!(eps < 1e8)) { if (info) *info = 1; throw Error{"K + eps*I is not positive definite for any jitter"}; }
+  }
+  if (jitter) *jitter = eps;
+  h->scal.ensure(256);
+  double* sc = h->scal.as<double>();                 // [0] logdetK (= sum log diag L, GPpref.py:131)  [2..3] per-iteration out
+  sum_log_kernel<<<1, 512, 0, h->s0>>>(m.diag, np, sc);
+  ++h->launches;
+  m.rows_total = 2 * np + TILE;
+  chol_inverse_lower(h, m);                                                // iK (GPpref.py:129)
+  h->aux2.ensure(static_cast<size_t>(np) * np * 8);
+  double* iK = h->aux2.as<double>();
+  {
+    const int64_t nt64 = np / 64;
+    mirror_lower_kernel<<<static_cast<unsigned>(nt64 * nt64), 256, 0, h->s0>>>(m.A, m.ld, iK, np, nt64);
+    GPB_CUDA(cudaGetLastError());
+    ++h->launches;
+  }
+  GPB_CUDA(cudaEventRecord(h->tev[1], h->s0));
+
+  // ---- Newton iterations (GPpref.py:138-155) ----
+  h->aux0.ensure(static_cast<size_t>(np) * 8 * 4);
+  double* f = h->aux0.as<double>();
+  double* f_new = f + np;
+  double* t = f_new + np;
+  GPB_CUDA(cudaMemsetAsync(f, 0, static_cast<size_t>(np) * 8 * 4, h->s0));
+  if (use_f0) GPB_CUDA(cudaMemcpyAsync(f, f_inout, n * 8, cudaMemcpyHostToDevice, h->s0));
+  const double isq = 1.0 / (sigma * std::sqrt(2.0)), i2v = isq * isq;      // GPpref.py:53-54
+  FactorMat g = m;
+  g.rows_total = np + 1;
+  double* brow = g.A + np * g.ld;
+  double* host = h->pinned(64);
+  int it = 0;
+  double last_lml = 0.0;
+  for (; it < max_iter;) {
+    pref_pair_kernel<<<static_cast<unsigned>((P + 255) / 256), 256, 0, h->s0>>>(pd.uvi, pd.y, P, f, isq, i2v, pd.dk, pd.wk);
+    scale_copy_lower_kernel<<<static_cast<unsigned>(np), 256, 0, h->s0>>>(iK, np, g.A, g.ld, nullptr, 0.0);
+    GPB_CUDA(cudaMemsetAsync(brow, 0, np * 8, h->s0));
+    pref_row_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, h->s0>>>(n, pd.gr, pd.dk, pd.wk, f, grad_mode, g.A,
+                                                                              g.ld, brow, nullptr, nullptr);
+    GPB_CUDA(cudaGetLastError());
+    h->launches += 3;
+    GPB_CUDA(cudaMemsetAsync(g.info, 0, 4, h->s0));
+    chol_sweep(h, g, true);                                  // G = L L^T, appended row <- L^-1 (W f + grad)
+    trsv_lt(h, g, brow, f_new);                              // f_new = G^-1 (W f + grad)   (GPpref.py:143)
+    launch_row_dot(iK, np, 0, f_new, 0, np, np, 0, t, 0, 1, h->s0);
+    pref_finish_kernel<<<1, 1024, 0, h->s0>>>(pd.uvi, pd.y, P, n, isq, f_new, f, t, sc, sc + 2);
+    GPB_CUDA(cudaGetLastError());
+    h->launches += 2;
+    GPB_CUDA(cudaMemcpyAsync(host, sc + 2, 16, cudaMemcpyDeviceToHost, h->s0));
+    GPB_CUDA(cudaMemcpyAsync(host + 2, g.info, 4, cudaMemcpyDeviceToHost, h->s0));
+    GPB_CUDA(cudaStreamSynchronize(h->s0));
+    const int ginfo = *reinterpret_cast<int*>(host + 2);
+    if (ginfo) { if (info) *info = ginfo; throw Error{"K^-1 + W is not positive definite"}; }
+    if (trace) { trace[2 * it] = host[0]; trace[2 * it + 1] = host[1]; }
+    last_lml = host[1];
+    ++it;
+    if (!(host[0] > delta_f)) break;                         // GPpref.py:140
+  }
+  GPB_CUDA(cudaEventRecord(h->tev[2], h->s0));
+  GPB_CUDA(cudaMemcpyAsync(f_inout, f, n * 8, cudaMemcpyDeviceToHost, h->s0));
+  GPB_CUDA(cudaStreamSynchronize(h->s0));
+  *lml = last_lml;
+  *iters = it;
+  for (float& x : h->timings) x = 0.f;
+  GPB_CUDA(cudaEventElapsedTime(&h->timings[0], h->tev[0], h->tev[1]));
+  GPB_CUDA(cudaEventElapsedTime(&h->timings[1], h->tev[1], h->tev[2]));
+  GPB_CUDA(cudaEventElapsedTime(&h->timings[4], h->tev[0], h->tev[2]));
+  h->lap_n = 0;
+  LAP_END
 }
-int gpb_pref_laplace(gpb_handle* h, const int64_t*, const double*, int64_t, const double*, double, double, int32_t,
-                     int32_t, int32_t, double*, double*, int32_t*, double*, double*, int32_t*) {
-  if (h) h->err = "pref_laplace not built yet";
-  return -4;
+
+int gpb_gpc_laplace(gpb_handle* h, const double* y, const double* khyp, int32_t link, double delta_f, int32_t max_iter,
+                    int32_t use_f0, double* f_inout, double* lml, int32_t* iters, double* trace, double* jitter,
+                    int32_t* info) {
+  LAP_BEGIN
+  GPB_REQUIRE(h->n > 0, "no training inputs: call gpb_set_train first");
+  GPB_REQUIRE(y && khyp && f_inout && lml && iters && max_iter > 0, "null argument");
+  const int64_t n = h->n, np = h->n_pad;
+  if (info) *info = 0;
+  h->lap_n = 0;
+  GPB_CUDA(cudaEventRecord(h->tev[0], h->s0));
+  FactorMat m = laplace_mat(h, np);
+  h->aux2.ensure(static_cast<size_t>(np) * np * 8);
+  double* K = h->aux2.as<double>();                      // full symmetric K + eps I
+  double eps = 1e-6;
+  const double *ell, *hyp2;
+  for (;;) {
+    upload_kernel_params(h, khyp, eps, &ell, &hyp2);
+    build_kernel_matrix(h, ell, hyp2, K, np, 0);
+    scale_copy_lower_kernel<<<static_cast<unsigned>(np), 256, 0, h->s0>>>(K, np, m.A, m.ld, nullptr, 0.0);
+    GPB_CUDA(cudaMemsetAsync(m.info, 0, 4, h->s0));
+    m.rows_total = np;
+    chol_sweep(h, m, true);                              // positive-definiteness check of K (jitter loop)
+    ++h->launches;
+    if (read_info(h, m) == 0) break;
+    eps *= 10.0;
+    if (!(eps < 1e8)) { if (info) *info = 1; throw Error{"K + eps*I is not positive definite for any jitter"}; }
+  }
+  if (jitter) *jitter = eps;
+  // vectors: f, f_new, b, sW, kb/t, a, y, g
+  h->aux0.ensure(static_cast<size_t>(np) * 8 * 8);
+  double* f = h->aux0.as<double>();
+  double *f_new = f + np, *b = f + 2 * np, *sW = f + 3 * np, *tv = f + 4 * np, *a = f + 5 * np, *yd = f + 6 * np, *gv = f + 7 * np;
+  GPB_CUDA(cudaMemsetAsync(f, 0, static_cast<size_t>(np) * 8 * 8, h->s0));
+  GPB_CUDA(cudaMemcpyAsync(yd, y, n * 8, cudaMemcpyHostToDevice, h->s0));
+  if (use_f0) GPB_CUDA(cudaMemcpyAsync(f, f_inout, n * 8, cudaMemcpyHostToDevice, h->s0));
+  h->scal.ensure(256);
+  double* sc = h->scal.as<double>();
+  FactorMat g = m;
+  g.rows_total = np + 1;
+  double* rrow = g.A + np * g.ld;
+  double* host = h->pinned(64);
+  const unsigned vb = static_cast<unsigned>((np + 255) / 256);
+  int it = 0;
+  double last_obj = 0.0;
+  for (; it < max_iter;) {
+    gpc_terms_kernel<<<vb, 256, 0, h->s0>>>(link, yd, f, n, np, sW, b, nullptr);                 // Alg 3.1 lines 4, 6
+    scale_copy_lower_kernel<<<static_cast<unsigned>(np), 256, 0, h->s0>>>(K, np, g.A, g.ld, sW, 1.0);   // B = I + sW K sW
+    launch_row_dot(K, np, 0, b, 0, np, np, 0, tv, 0, 1, h->s0);                                  // K b
+    vec_mul_kernel<<<vb, 256, 0, h->s0>>>(rrow, sW, tv, np);                                     // sW K b
+    GPB_CUDA(cudaGetLastError());
+    GPB_CUDA(cudaMemsetAsync(g.info, 0, 4, h->s0));
+    chol_sweep(h, g, true);                                                                      // L = chol(B), row <- L^-1 (sW K b)
+    trsv_lt(h, g, rrow, tv);                                                                     // L^T \ ( L \ (sW K b) )
+    gpc_a_kernel<<<vb, 256, 0, h->s0>>>(a, b, sW, tv, np);                                       // line 7
+    launch_row_dot(K, np, 0, a, 0, np, np, 0, f_new, 0, 1, h->s0);                               // line 8: f = K a
+    gpc_finish_kernel<<<1, 1024, 0, h->s0>>>(link, yd, n, a, f_new, f, sc + 2);
+    GPB_CUDA(cudaGetLastError());
+    h->launches += 7;
+    GPB_CUDA(cudaMemcpyAsync(host, sc + 2, 16, cudaMemcpyDeviceToHost, h->s0));
+    GPB_CUDA(cudaMemcpyAsync(host + 2, g.info, 4, cudaMemcpyDeviceToHost, h->s0));
+    GPB_CUDA(cudaStreamSynchronize(h->s0));
+    const int ginfo = *reinterpret_cast<int*>(host + 2);
+    if (ginfo) { if (info) *info = ginfo; throw Error{"I + sW K sW is not positive definite"}; }
+    if (trace) { trace[2 * it] = host[0]; trace[2 * it + 1] = host[1]; }
+    last_obj = host[1];
+    ++it;
+    if (!(host[0] > delta_f)) break;
+  }
+  // approximate log marginal likelihood at the returned f (Alg 3.1 line 10): W, L re-evaluated at f
+  gpc_terms_kernel<<<vb, 256, 0, h->s0>>>(link, yd, f, n, np, sW, b, gv);
+  scale_copy_lower_kernel<<<static_cast<unsigned>(np), 256, 0, h->s0>>>(K, np, g.A, g.ld, sW, 1.0);
+  GPB_CUDA(cudaMemsetAsync(g.info, 0, 4, h->s0));
+  g.rows_total = np;
+  chol_sweep(h, g, true);
+  sum_log_kernel<<<1, 512, 0, h->s0>>>(g.diag, np, sc);
+  GPB_CUDA(cudaGetLastError());
+  h->launches += 3;
+  GPB_CUDA(cudaEventRecord(h->tev[1], h->s0));
+  GPB_CUDA(cudaMemcpyAsync(host, sc, 8, cudaMemcpyDeviceToHost, h->s0));
+  GPB_CUDA(cudaMemcpyAsync(f_inout, f, n * 8, cudaMemcpyDeviceToHost, h->s0));
+  GPB_CUDA(cudaStreamSynchronize(h->s0));
+  *lml = last_obj - host[0];
+  *iters = it;
+  for (float& x : h->timings) x = 0.f;
+  GPB_CUDA(cudaEventElapsedTime(&h->timings[4], h->tev[0], h->tev[1]));
+  // state for gpb_gpc_predict: L and Dinv (in h->A / h->Dinv), sW, grad, kernel parameters
+  h->lap_n = n;
+  h->lap_link = link;
+  h->lap_khyp.assign(khyp, khyp + h->d + 1);
+  LAP_END
 }
-int gpb_pref_derivatives(gpb_handle* h, const int64_t*, const double*, int64_t, int64_t, const double*, double,
-                         int32_t, double*, double*) {
-  if (h) h->err = "pref_derivatives not built yet";
-  return -4;
+
+int gpb_gpc_predict(gpb_handle* h, const double* Z, int64_t mz, double* mu, double* var, double* prob) {
+  LAP_BEGIN
+  GPB_REQUIRE(h->lap_n == h->n && h->n > 0, "no Laplace state on this handle: call gpb_gpc_laplace first");
+  GPB_REQUIRE(Z && mu && var && prob && mz > 0, "null argument");
+  const int64_t np = h->n_pad;
+  const int nt = static_cast<int>(np / TILE);
+  FactorMat m = laplace_mat(h, np);            // same buffers: L of B is still in rows [0, np)
+  double* f = h->aux0.as<double>();
+  const double *sW = f + 3 * np, *gv = f + 7 * np;
+  const double *ell, *hyp2;
+  upload_kernel_params(h, h->lap_khyp.data(), 0.0, &ell, &hyp2);
+  const double sf2 = h->lap_khyp[h->d];
+  double* rows = m.A + (np + TILE) * m.ld;     // test rows live where grad.cu keeps U
+  const int64_t cap = np;                      // rows available there
+  h->outv.ensure(static_cast<size_t>(cap) * 8 * 3);
+  double* o = h->outv.as<double>();
+  for (int64_t z0 = 0; z0 < mz; z0 += cap) {
+    const int64_t mc = mz - z0 < cap ? mz - z0 : cap;
+    const int64_t mp64 = round_up(mc, 64);
+    h->Zd.ensure(static_cast<size_t>(mc) * h->d * 8);
+    GPB_CUDA(cudaMemcpyAsync(h->Zd.p, Z + z0 * h->d, static_cast<size_t>(mc) * h->d * 8, cudaMemcpyHostToDevice, h->s0));
+    h->ZsT.ensure(static_cast<size_t>(h->d) * mp64 * 8);
+    h->zsq.ensure(static_cast<size_t>(mp64) * 8);
+    launch_se_prep(h->Zd.as<double>(), mc, h->d, ell, h->ZsT.as<double>(), mp64, h->zsq.as<double>(), 1, 0, 0, 0, h->s0);
+    SeArgs a{};
+    a.rT = h->ZsT.as<double>(); a.r_ld = mp64; a.r_sq = h->zsq.as<double>(); a.n_rows_valid = mc;
+    a.cT = h->XsT.as<double>(); a.c_ld = np; a.c_sq = h->sq.as<double>(); a.n_cols_valid = h->n;
+    a.d = h->d; a.out = rows; a.ld = m.ld; a.rows_pad = mp64; a.cols_pad = np;
+    a.hyp_dev = hyp2; a.mode = 2; a.clip = 1;
+    launch_se_build(a, 1, h->s0);                                                   // k*^T rows
+    launch_row_dot(rows, m.ld, 0, gv, 0, mc, np, 0, o, 0, 1, h->s0);                // Alg 3.2 line 4: k*^T grad
+    scale_cols_kernel<<<static_cast<unsigned>(mc), 256, 0, h->s0>>>(rows, m.ld, np, sW);
+    GPB_CUDA(cudaGetLastError());
+    h->launches += 4;
+    m.rows_total = np + TILE + mc;
+    SweepPlan plan;
+    plan.factor = false;
+    plan.extra_tile0 = nt + 1;
+    plan.extra_tiles = static_cast<int>((mc + TILE - 1) / TILE);
+    chol_sweep(h, m, plan);                                                         // rows <- (L^-1 sW k*)^T  (line 5)
+    gpc_predict_finish_kernel<<<static_cast<unsigned>(mc), 256, 0, h->s0>>>(rows, m.ld, np, sf2, h->lap_link, o, o + cap, o + 2 * cap);
+    GPB_CUDA(cudaGetLastError());
+    ++h->launches;
+    GPB_CUDA(cudaMemcpyAsync(mu + z0, o, mc * 8, cudaMemcpyDeviceToHost, h->s0));
+    GPB_CUDA(cudaMemcpyAsync(var + z0, o + cap, mc * 8, cudaMemcpyDeviceToHost, h->s0));
+    GPB_CUDA(cudaMemcpyAsync(prob + z0, o + 2 * cap, mc * 8, cudaMemcpyDeviceToHost, h->s0));
+    GPB_CUDA(cudaStreamSynchronize(h->s0));
+  }
+  LAP_END
 }
-}
+
+}  // extern "C"

@@ -77,6 +77,7 @@ def calc_laplace(x, y, loghyp, link='probit', delta_f=1e-6, f=None, max_iter=100
     f_error = delta_f + 1
     it = 0
     trace = []
+    a = np.zeros(n)
     while f_error > delta_f and it < max_iter:
         lp, g, W = terms(y, f)
         sW = np.sqrt(W)
@@ -92,11 +93,10 @@ def calc_laplace(x, y, loghyp, link='probit', delta_f=1e-6, f=None, max_iter=100
         lp_new = terms(y, f)[0]
         trace.append((float(f_error), float(-0.5 * a @ f + np.sum(lp_new))))
     # Approximate log marginal likelihood at the returned f (Alg 3.1 line 10): W and L are
-    # re-evaluated at the final f so that the value is a function of f alone.
+    # re-evaluated at the final f; a is the last iteration's (f = K a exactly, line 8).
     lp, g, W = terms(y, f)
     sW = np.sqrt(W)
     L = np.linalg.cholesky(np.eye(n) + sW[:, None] * K * sW[None, :])
-    a = np.linalg.solve(K, f)
     lml = -0.5 * a @ f + np.sum(lp) - np.sum(np.log(np.diag(L)))
     if return_state:
         return f, lml, dict(K=K, L=L, sW=sW, g=g, it=it, trace=trace, eps=eps)

@@ -62,8 +62,11 @@ class ProbitPrefOracle:
         """GPpref.py:56-58: y * (f[v] - f[u]) / (sqrt(2) sigma); shapes (P,1)."""
         return y * (self.isqrt2sig * (f[uvi[:, 1]] - f[uvi[:, 0]]))
 
-    def derivatives(self, uvi, y, f):
-        """GPpref.py:68-88 including the last-write-wins gradient (quirk 1)."""
+    def derivatives(self, uvi, y, f, accumulate=False):
+        """GPpref.py:68-88 including the last-write-wins gradient (quirk 1).
+
+        accumulate=True (NOT the reference) sums the contributions of repeated items instead,
+        which makes the loop a true Newton iteration; used to test the product's opt-in mode."""
         nx = len(f)
         z = self.z_k(uvi, f, y)
         phi_z = ndtr(z)                                      # GPpref.py:71
@@ -72,8 +75,12 @@ class ProbitPrefOracle:
         d = y * self.isqrt2sig * n_z / phi_z                 # GPpref.py:76
         # GPpref.py:77-78.  ``a[idx] += v`` is ``a[idx] = a[idx] + v``: one gather, one add,
         # one scatter; for a repeated index the LAST occurrence is the value that stays.
-        g[uvi[:, 0]] = g[uvi[:, 0]] - d
-        g[uvi[:, 1]] = g[uvi[:, 1]] + d
+        if accumulate:
+            np.add.at(g, (uvi[:, 0], 0), -d[:, 0])
+            np.add.at(g, (uvi[:, 1], 0), d[:, 0])
+        else:
+            g[uvi[:, 0]] = g[uvi[:, 0]] - d
+            g[uvi[:, 1]] = g[uvi[:, 1]] + d
         inner = -self.i2var * (z * n_z / phi_z + (n_z / phi_z) ** 2)   # GPpref.py:80
         W = np.zeros((nx, nx), dtype=float)                  # GPpref.py:81
         w = -inner[:, 0]                                     # W[..] -= ddpy_df  ==  += w
@@ -108,7 +115,7 @@ def gradient_last_writer(uvi, n):
     return ku, kv
 
 
-def calc_laplace(x, uvi, y, loghyp, delta_f=1e-6, f=None, max_iter=None, return_trace=False):
+def calc_laplace(x, uvi, y, loghyp, delta_f=1e-6, f=None, max_iter=None, return_trace=False, accumulate=False):
     """``PreferenceGaussianProcess.calc_laplace`` (GPpref.py:112-157).
 
     ``max_iter`` (not in the reference, which has no cap) bounds test/bench runs.
@@ -138,7 +145,7 @@ def calc_laplace(x, uvi, y, loghyp, delta_f=1e-6, f=None, max_iter=None, return_
     trace = []
     lml = None
     while f_error > delta_f:                                 # GPpref.py:140
-        W, g = lik.derivatives(uvi, y, f)                    # GPpref.py:141
+        W, g = lik.derivatives(uvi, y, f, accumulate)        # GPpref.py:141
         G = iK + W                                           # GPpref.py:142
         f_new = np.matmul(np.linalg.inv(G), np.matmul(W, f) + g)   # GPpref.py:143
         lml = lik.log_marginal(uvi, y, f_new, iK, logdetK)   # GPpref.py:144
