@@ -1,0 +1,4 @@
+"""Shim: `import GPc` resolves to the B200 implementation."""
+from gptest_b200.GPc import *  # noqa: F401,F403
+from gptest_b200 import GPc as _impl
+__all__ = [n for n in dir(_impl) if not n.startswith('_')]
