@@ -223,6 +223,7 @@ int gpb_set_option(gpb_handle* h, const char* name, int64_t value) {
   if (!strcmp(name, "lookahead")) h->lookahead = value != 0;
   else if (!strcmp(name, "nb_tiles")) h->nb_tiles = static_cast<int>(value < 1 ? 1 : (value > 8 ? 8 : value));
   else if (!strcmp(name, "batch_chunk")) h->batch_chunk = value;
+  else if (!strcmp(name, "small_tile_threshold")) h->small_tile_threshold = value;
   else { h->err = std::string("unknown option ") + name; return -1; }
   return 0;
 }
@@ -411,7 +412,7 @@ int gpb_potrf_lower_dev(gpb_handle* h, double* A_dev, int64_t n, int64_t lda, in
   GPB_CUDA(cudaMemsetAsync(m.info, 0, 4, h->s0));
   finalize_factor_mat(m);
   // the tensor map addresses columns [0, lda): restrict to the matrix itself
-  make_tensor_map(&m.mapA, m.A, n, n, 1, lda, n * lda);
+  make_tile_maps(&m.mapA, m.A, n, n, 1, lda, n * lda);
   tic(h, 0);
   tic(h, 1);
   chol_sweep(h, m, true);
@@ -462,7 +463,7 @@ int gpb_dgemm_nt_dev(gpb_handle* h, double* C, int64_t ldc, const double* A, int
   a.C = C; a.ldc = ldc; a.c_batch_stride = 0; a.rows_total = static_cast<int>(M);
   a.j0 = 0; a.j1 = static_cast<int>(N / TILE); a.R = static_cast<int>(M / TILE); a.tri = 0; a.i0 = 0;
   a.ka0 = 0; a.kb0 = 0; a.nk = static_cast<int>(K / GEMM_KB); a.b_row0 = 0; a.epi = epi;
-  launch_dmma_gemm(ma, mb, a, 1, h->s0);
+  launch_dmma_gemm(ma, mb, a, 1, h->s0, 128);
   ++h->launches;
   GPB_API_END
 }

@@ -39,7 +39,7 @@ static EncodeTiledFn encode_fn() {
 // 3-D fp64 tensor map {cols, rows, batch}; box = {16 doubles (128 B), 128 rows, 1}; 128B swizzle;
 // out-of-bounds rows read as zero (partial last row tile of the appended rows).
 void make_tensor_map(CUtensorMap* map, const double* base, int64_t cols, int64_t rows, int64_t batch,
-                     int64_t row_pitch, int64_t batch_pitch) {
+                     int64_t row_pitch, int64_t batch_pitch, int box_rows) {
   GPB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "matrix base must be 16-byte aligned");
   GPB_REQUIRE(row_pitch % 2 == 0, "leading dimension must be even (16-byte row pitch)");
   if (batch_pitch <= 0) batch_pitch = rows * row_pitch;
@@ -47,7 +47,7 @@ void make_tensor_map(CUtensorMap* map, const double* base, int64_t cols, int64_t
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows),
                         static_cast<cuuint64_t>(batch < 1 ? 1 : batch)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_pitch) * 8, static_cast<cuuint64_t>(batch_pitch) * 8};
-  cuuint32_t box[3] = {GEMM_KB, TILE, 1};
+  cuuint32_t box[3] = {GEMM_KB, static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides,
                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -55,10 +55,24 @@ void make_tensor_map(CUtensorMap* map, const double* base, int64_t cols, int64_t
   if (r != CUDA_SUCCESS) throw Error{"cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r))};
 }
 
+void make_tile_maps(TileMaps* maps, const double* base, int64_t cols, int64_t rows, int64_t batch,
+                    int64_t row_pitch, int64_t batch_pitch) {
+  make_tensor_map(&maps->m128, base, cols, rows, batch, row_pitch, batch_pitch, 128);
+  make_tensor_map(&maps->m64, base, cols, rows, batch, row_pitch, batch_pitch, 64);
+}
+
 void finalize_factor_mat(FactorMat& m) {
   GPB_REQUIRE(m.n_pad % TILE == 0, "n_pad must be a multiple of 128");
-  make_tensor_map(&m.mapA, m.A, m.ld, m.rows_total, m.batch, m.ld, m.batch_stride);
-  make_tensor_map(&m.mapD, m.Dinv, TILE, m.n_pad, m.batch, TILE, m.dinv_bs);
+  make_tile_maps(&m.mapA, m.A, m.ld, m.rows_total, m.batch, m.ld, m.batch_stride);
+  make_tile_maps(&m.mapD, m.Dinv, TILE, m.n_pad, m.batch, TILE, m.dinv_bs);
+}
+
+GemmArgs gemm_args_to_64(const GemmArgs& a) {
+  GemmArgs b = a;
+  b.j0 = 2 * a.j0; b.j1 = 2 * a.j1; b.i_off = 2 * a.i_off; b.i0 = 2 * a.i0;
+  const int r64 = (a.rows_total + 63) / 64;
+  b.R = 2 * a.R < r64 ? 2 * a.R : r64;
+  return b;
 }
 
 namespace {
@@ -92,14 +106,38 @@ struct Sweep {
     }
     return a;
   }
-  // A[i,k] <- A[i,k] * W_k^T for the rows below tile (k,k) (and the appended rows)
+  // 64-tiles when the launch cannot fill the machine with 128-tiles (panel critical path, tail)
+  void launch(const GemmArgs& a, const TileMaps& ma, const TileMaps& mb, cudaStream_t st) {
+    const int n128 = gemm_region_tiles(a);
+    if (n128 <= 0) return;
+    if (static_cast<int64_t>(n128) * m.batch < h->small_tile_threshold) {
+      launch_dmma_gemm(ma.m64, mb.m64, gemm_args_to_64(a), m.batch, st, 64);
+    } else {
+      launch_dmma_gemm(ma.m128, mb.m128, a, m.batch, st, 128);
+    }
+    ++h->launches;
+  }
+  // A[i,k] <- A[i,k] * W_k^T for the rows below tile (k,k) (and the appended rows).  In place: a CTA
+  // must own all 128 output columns of its rows (they are also its A operand), so the small-tile
+  // variant is 64 rows x 128 columns.
   void trsm(int k, cudaStream_t st) {
     GemmArgs a = base(k);
-    a.j0 = k; a.j1 = k + 1; a.i_off = 1;
+    a.tri = 0;                                  // one tile column: rows [first, R)
+    a.i0 = factor ? k + 1 : x0;
+    a.j0 = k; a.j1 = k + 1;
     a.ka0 = k * TILE; a.kb0 = 0; a.nk = TILE / GEMM_KB; a.b_row0 = 0;
     a.epi = 0;
-    if (gemm_region_tiles(a) <= 0) return;
-    launch_dmma_gemm(m.mapA, m.mapD, a, m.batch, st);
+    const int n128 = gemm_region_tiles(a);
+    if (n128 <= 0) return;
+    if (static_cast<int64_t>(n128) * m.batch < h->small_tile_threshold) {
+      GemmArgs b = a;
+      b.i0 = 2 * a.i0;
+      const int r64 = (a.rows_total + 63) / 64;
+      b.R = 2 * a.R < r64 ? 2 * a.R : r64;
+      launch_dmma_gemm(m.mapA.m64, m.mapD.m128, b, m.batch, st, 64128);
+    } else {
+      launch_dmma_gemm(m.mapA.m128, m.mapD.m128, a, m.batch, st, 128);
+    }
     ++h->launches;
   }
   // A[i,j] -= sum_{k in [ka,kb)} A[i,k] A[j,k]^T for tile columns j in [c0,c1), rows i >= j
@@ -109,9 +147,7 @@ struct Sweep {
     a.j0 = c0; a.j1 = c1; a.i_off = 0;
     a.ka0 = ka * TILE; a.kb0 = ka * TILE; a.nk = (kb - ka) * TILE / GEMM_KB; a.b_row0 = 0;
     a.epi = 1;
-    if (gemm_region_tiles(a) <= 0) return;
-    launch_dmma_gemm(m.mapA, m.mapA, a, m.batch, st);
-    ++h->launches;
+    launch(a, m.mapA, m.mapA, st);
   }
   void panel(int kb, int kend, cudaStream_t st) {
     for (int k = kb; k < kend; ++k) {

@@ -1,6 +1,6 @@
 // dmma_gemm.cu - the kernel the factorisation spends its time in.
 //
-// C(it,jt) (op)= sum_k A(it,k) * B(jt,k)^T on 128x128 tiles of row-major fp64 matrices, used for
+// C(it,jt) (op)= sum_k A(it,k) * B(jt,k)^T on square tiles of row-major fp64 matrices, used for
 //   - the trailing SYRK/GEMM update of the blocked Cholesky (np.linalg.cholesky, GPr.py:62),
 //   - the panel TRSM written as a product with the inverted diagonal tile,
 //   - the fused forward solves (rows appended under K), TRTRI/LAUUM of the gradient stage.
@@ -8,15 +8,16 @@
 // B200 mapping
 //   * tcgen05 has no f64 kind: the FP64 tensor path on sm_100a is the warp-level
 //     mma.sync.m8n8k4 (SASS DMMA.8x8x4), operands in registers.
-//   * operand slabs (128 rows x 16 doubles = 128-byte rows) are brought in by TMA
+//   * operand slabs (tile rows x 16 doubles = 128-byte rows) are brought in by TMA
 //     (cp.async.bulk.tensor, SASS UTMALDG) with the 128B swizzle through a 4-stage
-//     full/empty mbarrier ring; one producer warp, eight DMMA consumer warps (2 x 4, each
-//     64 x 32 of the tile = 32 DMMA accumulators).
+//     full/empty mbarrier ring; one producer warp, WM x WN DMMA consumer warps.
 //   * fragment rows are taken with a stride of two tile rows ("parity" fragments): under the
 //     128B swizzle the 16 lanes of a half warp then read 8 distinct 16-byte chunks over 4 rows
 //     = all 32 banks once, so every 64-bit fragment load is conflict free.
-//   * per 16-wide slab a warp issues 128 DMMA for 48 LDS.64: the FP64 tensor pipe is the only
-//     busy unit; shared-memory and issue bandwidth stay below 20 %.
+//   * two instantiations: 128x128 tiles (8 consumer warps of 64x32, 1 CTA/SM) for throughput -
+//     per 16-wide slab a warp issues 128 DMMA for 48 LDS.64, the FP64 tensor pipe is the only
+//     busy unit - and 64x64 tiles (4 consumer warps of 32x32, 3 CTAs/SM) for launches that are
+//     on the panel's critical path or too small to fill 148 SMs with 128-tiles.
 #include "gpb_kernels.cuh"
 
 namespace gpb {
@@ -39,12 +40,23 @@ __device__ __forceinline__ void decode_tile(const GemmArgs& p, int idx, int& it,
   }
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// BM x BN output tile per CTA (rows in units of BM, columns in units of BN)
+template <int BM, int BN, int WM, int WN, int MINB>
+__global__ void __launch_bounds__(WM * WN * 32, MINB)
 dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const GemmArgs p) {
+  constexpr int NCW = WM * WN;               // consumer warps
+  constexpr int BMW = BM / WM;               // warp tile rows
+  constexpr int BNW = BN / WN;               // warp tile columns
+  constexpr int GM = BMW / 16;               // 16-row groups per warp (two parity fragments each)
+  constexpr int GN = BNW / 16;
+  constexpr int SLAB_A = BM * GEMM_KB * 8;   // bytes of one operand slab
+  constexpr int SLAB_B = BN * GEMM_KB * 8;
+  constexpr int STAGE = SLAB_A + SLAB_B;
+
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * STAGE);
   uint64_t* empty = full + GEMM_STAGES;
 
   const int warp = threadIdx.x >> 5;
@@ -52,56 +64,57 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const int batch = blockIdx.y;
   int it, jt;
   decode_tile(p, blockIdx.x, it, jt);
-  const int ka0 = p.k_from_row ? it * TILE : p.ka0;
-  const int kb0 = p.k_from_row ? it * TILE : p.kb0;
-  const int nk = p.k_from_row ? (p.k_tiles - it) * (TILE / GEMM_KB) : p.nk;
+  const int nk = p.k_from_row ? (p.k_end - it * BM) / GEMM_KB : p.nk;
 
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < GEMM_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], GEMM_CONSUMER_WARPS);
+      mbar_init(&empty[s], NCW);
     }
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (warp == GEMM_CONSUMER_WARPS) {
-    // ---------------- TMA producer: one elected lane ----------------
-    if (lane == 0) {
-      tma_prefetch_desc(&mapA);
-      tma_prefetch_desc(&mapB);
-      const int arow = p.a_row0 + it * TILE;
-      const int brow = p.b_row0 + jt * TILE;
-      for (int s = 0; s < nk; ++s) {
-        const int st = s % GEMM_STAGES;
-        if (s >= GEMM_STAGES) mbar_wait(&empty[st], ((s / GEMM_STAGES) - 1) & 1);
-        uint8_t* dst = smem + st * GEMM_STAGE_BYTES;
-        mbar_arrive_expect_tx(&full[st], GEMM_STAGE_BYTES);
-        tma_load_3d(dst, &mapA, &full[st], ka0 + GEMM_KB * s, arow, batch);
-        tma_load_3d(dst + TILE * GEMM_KB * 8, &mapB, &full[st], kb0 + GEMM_KB * s, brow, batch);
-      }
-    }
-    return;
+  // ---------------- TMA producer duty: the elected lane of warp 0 ----------------
+  // (no dedicated producer warp: registers are allocated in groups of four warps, a ninth warp
+  //  would cap the DMMA warps at 168 registers and spill the accumulators)
+  const bool producer = (threadIdx.x == 0);
+  const int ka0 = p.k_from_row ? it * BM : p.ka0;
+  const int kb0 = p.k_from_row ? it * BM : p.kb0;
+  const int arow = p.a_row0 + it * BM;
+  const int brow = p.b_row0 + jt * BN;
+  auto issue = [&](int s) {
+    const int st = s % GEMM_STAGES;
+    uint8_t* dst = smem + st * STAGE;
+    mbar_arrive_expect_tx(&full[st], STAGE);
+    tma_load_3d(dst, &mapA, &full[st], ka0 + GEMM_KB * s, arow, batch);
+    tma_load_3d(dst + SLAB_A, &mapB, &full[st], kb0 + GEMM_KB * s, brow, batch);
+  };
+  if (producer) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    for (int s = 0; s < GEMM_STAGES && s < nk; ++s) issue(s);
   }
 
   // ---------------- DMMA consumers ----------------
-  const int wm = warp >> 2;        // 0..1 : 64-row half of the tile
-  const int wn = warp & 3;         // 0..3 : 32-column quarter of the tile
+  const int wm = warp / WN;
+  const int wn = warp % WN;
   const int g = lane >> 2;         // fragment row (A) / column (B)
   const int t = lane & 3;          // fragment k index
   const int th = t >> 1;
 
-  double* Cb = p.C + static_cast<int64_t>(batch) * p.c_batch_stride;
-  const int64_t row_base = static_cast<int64_t>(it) * TILE + wm * 64;
-  const int64_t col_base = static_cast<int64_t>(jt) * TILE + wn * 32;
   if (p.epi == 1) {
-    // pull this warp's 64 x 32 piece of C towards L2 while the k loop runs
+    // pull this warp's piece of C towards L2 while the k loop runs (128-byte lines)
+    const double* Cp = p.C + static_cast<int64_t>(batch) * p.c_batch_stride;
+    const int64_t rb = static_cast<int64_t>(it) * BM + wm * BMW;
+    const int64_t cb = static_cast<int64_t>(jt) * BN + wn * BNW;
+    constexpr int LPR = BNW / 16;                       // lines per row
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < BMW * LPR / 32; ++q) {
       const int idx = lane + 32 * q;
-      const int64_t row = row_base + (idx >> 1);
-      if (row < p.rows_total) prefetch_l2(Cb + row * p.ldc + col_base + (idx & 1) * 16);
+      const int64_t row = rb + idx / LPR;
+      if (row < p.rows_total) prefetch_l2(Cp + row * p.ldc + cb + (idx % LPR) * 16);
     }
   }
 
@@ -110,55 +123,66 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
   for (int par = 0; par < 2; ++par) {
     xr[par] = ((g & 3) << 1) | par;
-    a_off[par] = (wm * 64 + 2 * g + par) * 128 + (t & 1) * 8;
-    b_off[par] = (wn * 32 + 2 * g + par) * 128 + (t & 1) * 8;
+    a_off[par] = (wm * BMW + 2 * g + par) * 128 + (t & 1) * 8;
+    b_off[par] = (wn * BNW + 2 * g + par) * 128 + (t & 1) * 8;
   }
 
-  double acc[8][4][2];
+  double acc[2 * GM][2 * GN][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 2 * GM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < 2 * GN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   for (int s = 0; s < nk; ++s) {
     const int st = s % GEMM_STAGES;
+    if (producer && s >= 1 && s - 1 + GEMM_STAGES < nk) {
+      // refill the slot of slab s-1 (this warp has just left it) once every warp has released it
+      mbar_wait(&empty[(s - 1) % GEMM_STAGES], ((s - 1) / GEMM_STAGES) & 1);
+      issue(s - 1 + GEMM_STAGES);
+    }
+    __syncwarp();
     mbar_wait(&full[st], (s / GEMM_STAGES) & 1);
-    const uint8_t* sa = smem + st * GEMM_STAGE_BYTES;
-    const uint8_t* sb = sa + TILE * GEMM_KB * 8;
+    const uint8_t* sa = smem + st * STAGE;
+    const uint8_t* sb = sa + SLAB_A;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      double af[8], bf[4];
+      double af[2 * GM], bf[2 * GN];
 #pragma unroll
       for (int par = 0; par < 2; ++par) {
         const uint32_t chunk = ((2 * kk + th) ^ xr[par]) << 4;
 #pragma unroll
-        for (int grp = 0; grp < 4; ++grp)
+        for (int grp = 0; grp < GM; ++grp)
           af[grp * 2 + par] = *reinterpret_cast<const double*>(sa + a_off[par] + grp * 2048 + chunk);
 #pragma unroll
-        for (int grp = 0; grp < 2; ++grp)
+        for (int grp = 0; grp < GN; ++grp)
           bf[grp * 2 + par] = *reinterpret_cast<const double*>(sb + b_off[par] + grp * 2048 + chunk);
       }
 #pragma unroll
-      for (int mi = 0; mi < 8; ++mi)
+      for (int mi = 0; mi < 2 * GM; ++mi)
 #pragma unroll
-        for (int nj = 0; nj < 4; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], af[mi], bf[nj]);
+        for (int nj = 0; nj < 2 * GN; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], af[mi], bf[nj]);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);
   }
 
   // ---------------- epilogue: each lane owns 4 consecutive columns per (row, column group) -------
+  // (addresses are recomputed here so that nothing but the accumulators lives across the k loop)
+  asm volatile("" : "+r"(it), "+r"(jt));
+  double* Cb = p.C + static_cast<int64_t>(batch) * p.c_batch_stride;
+  const int64_t row_base = static_cast<int64_t>(it) * BM + wm * BMW;
+  const int64_t col_base = static_cast<int64_t>(jt) * BN + wn * BNW;
   // fragment (grp_m, par_m) row g  -> tile row 16 grp_m + 2 g + par_m
   // fragment (grp_n, par_n) col 2t+e -> tile col 16 grp_n + 4 t + 2 e + par_n
 #pragma unroll
-  for (int gm = 0; gm < 4; ++gm) {
+  for (int gm = 0; gm < GM; ++gm) {
 #pragma unroll
     for (int pm = 0; pm < 2; ++pm) {
       const int64_t row = row_base + 16 * gm + 2 * g + pm;
       if (row < p.rows_total) {
         const int mi = gm * 2 + pm;
 #pragma unroll
-        for (int gn = 0; gn < 2; ++gn) {
+        for (int gn = 0; gn < GN; ++gn) {
           double* ptr = Cb + row * p.ldc + col_base + 16 * gn + 4 * t;
           double2 lo = make_double2(acc[mi][gn * 2][0], acc[mi][gn * 2 + 1][0]);
           double2 hi = make_double2(acc[mi][gn * 2][1], acc[mi][gn * 2 + 1][1]);
@@ -188,19 +212,30 @@ int gemm_region_tiles(const GemmArgs& a) {
   return ncols * (a.R - a.i0);
 }
 
+constexpr int smem_bytes(int bm, int bn) { return GEMM_STAGES * (bm + bn) * GEMM_KB * 8 + 1024 + 256; }
+
 void dmma_gemm_init() {
-  GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                GEMM_SMEM_BYTES));
+  GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<128, 128, 2, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                smem_bytes(128, 128)));
+  GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<64, 64, 2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                smem_bytes(64, 64)));
+  GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<64, 128, 2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                smem_bytes(64, 128)));
 }
 
 void launch_dmma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmArgs a, int batch,
-                      cudaStream_t st) {
+                      cudaStream_t st, int tile) {
   const int ntiles = gemm_region_tiles(a);
   GPB_REQUIRE(ntiles >= 0, "dmma_gemm: empty column in trapezoid region");
   if (ntiles == 0 || (a.nk == 0 && !a.k_from_row)) return;
   a.ntiles = ntiles;
   dim3 grid(ntiles, batch, 1);
-  dmma_gemm_nt_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(mapA, mapB, a);
+  if (tile == 128)
+    dmma_gemm_nt_kernel<128, 128, 2, 4, 1><<<grid, 8 * 32, smem_bytes(128, 128), st>>>(mapA, mapB, a);
+  else if (tile == 64)
+    dmma_gemm_nt_kernel<64, 64, 2, 2, 3><<<grid, 4 * 32, smem_bytes(64, 64), st>>>(mapA, mapB, a);
+  else   // 64 x 128: rows in units of 64, columns in units of 128 (mapA with 64-row boxes, mapB with 128-row boxes)
+    dmma_gemm_nt_kernel<64, 128, 2, 2, 2><<<grid, 4 * 32, smem_bytes(64, 128), st>>>(mapA, mapB, a);
   GPB_CUDA(cudaGetLastError());
 }
 

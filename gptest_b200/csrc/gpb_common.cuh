@@ -16,7 +16,7 @@ constexpr int TILE = 128;          // tile edge of the blocked factorisation (el
 constexpr int GEMM_KB = 16;        // k-slab per pipeline stage: 16 doubles = one 128-byte TMA row
 constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_CONSUMER_WARPS = 8;
-constexpr int GEMM_THREADS = (GEMM_CONSUMER_WARPS + 1) * 32;   // + 1 TMA producer warp
+constexpr int GEMM_THREADS = GEMM_CONSUMER_WARPS * 32;
 constexpr int GEMM_STAGE_BYTES = 2 * TILE * GEMM_KB * 8;       // A slab + B slab = 32 KiB
 constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 

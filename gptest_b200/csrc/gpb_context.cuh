@@ -39,7 +39,7 @@ struct FactorMat {
   double* diag = nullptr;    // per batch n_pad
   int64_t diag_bs = 0;
   int* info = nullptr;       // per batch
-  CUtensorMap mapA, mapD;
+  TileMaps mapA, mapD;
 };
 
 }  // namespace gpb
@@ -56,6 +56,7 @@ struct gpb_handle {
   int lookahead = 1;
   int nb_tiles = 2;
   int64_t batch_chunk = 0;       // 0 = auto
+  int64_t small_tile_threshold = 296;   // launches with fewer 128-tiles than this use 64-tiles
 
   // training data (GPr.py:25-26 keeps trainInput / trainTarget on the object)
   int64_t n = 0, n_pad = 0;
@@ -88,7 +89,9 @@ struct gpb_handle {
 namespace gpb {
 
 void make_tensor_map(CUtensorMap* map, const double* base, int64_t cols, int64_t rows, int64_t batch,
-                     int64_t row_pitch_elems, int64_t batch_pitch_elems);
+                     int64_t row_pitch_elems, int64_t batch_pitch_elems, int box_rows = TILE);
+void make_tile_maps(TileMaps* maps, const double* base, int64_t cols, int64_t rows, int64_t batch,
+                    int64_t row_pitch_elems, int64_t batch_pitch_elems);
 
 // Blocked right-looking Cholesky sweep (see chol.cu).  factor == true: factor the symmetric part
 // and carry the extra rows along; factor == false: the symmetric part already holds L (and Dinv

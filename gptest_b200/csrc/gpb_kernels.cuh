@@ -16,17 +16,26 @@ struct GemmArgs {
   // tile region.  tri == 1: columns jt in [j0, j1), rows it in [jt + i_off, R) (a trapezoid,
   // enumerated column by column).  tri == 0: rows it in [i0, R) for every column.
   int j0, j1, R, tri, i_off, i0;
-  // operands.  A slab s: mapA box at (ka0 + 16 s, a_row0 + 128 it, batch);
-  //            B slab s: mapB box at (kb0 + 16 s, b_row0 + 128 jt, batch).
-  // k_from_row != 0: the k range of tile (it, jt) starts at tile column `it` (operands that are
-  // upper triangular: U U^T products), i.e. ka0 = kb0 = 128 it and nk = 8 (k_tiles - it).
-  int ka0, kb0, nk, a_row0, b_row0, k_from_row, k_tiles;
+  // All tile coordinates (j0, j1, R, i_off, i0, it, jt) are in units of the kernel's tile edge T
+  // (128 or 64); row / k offsets are in elements.
+  // operands.  A slab s: mapA box at (ka0 + 16 s, a_row0 + T it, batch);
+  //            B slab s: mapB box at (kb0 + 16 s, b_row0 + T jt, batch).
+  // k_from_row != 0: the k range of tile (it, jt) starts at column T*it (operands that are
+  // upper triangular: U U^T products), i.e. ka0 = kb0 = T it and nk = (k_end - T it) / 16.
+  int ka0, kb0, nk, a_row0, b_row0, k_from_row, k_end;
   int epi;                  // 0: C = acc     1: C = C - acc
   int ntiles;               // gridDim.x
 };
 int gemm_region_tiles(const GemmArgs& a);       // host: number of tiles of the region
+// one tensor map per tile edge: the TMA box height is part of the map
+struct TileMaps {
+  CUtensorMap m128, m64;
+  const CUtensorMap& get(int tile) const { return tile == 128 ? m128 : m64; }
+};
 void launch_dmma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmArgs a, int batch,
-                      cudaStream_t st);
+                      cudaStream_t st, int tile);
+// region given in 128-tile units -> the same region in 64-tile units
+GemmArgs gemm_args_to_64(const GemmArgs& a);
 void dmma_gemm_init();                           // sets the dynamic smem attribute once
 
 // ---------------------------------------------------------------------------------------

@@ -222,8 +222,8 @@ void chol_inverse_lower(gpb_handle* h, FactorMat& m) {
   a.C = m.A; a.ldc = m.ld; a.c_batch_stride = m.batch_stride; a.rows_total = static_cast<int>(np);
   a.j0 = 0; a.j1 = nt; a.R = nt; a.tri = 1; a.i_off = 0;
   a.a_row0 = a.b_row0 = static_cast<int>(np + TILE);
-  a.k_from_row = 1; a.k_tiles = nt; a.epi = 0;
-  launch_dmma_gemm(m.mapA, m.mapA, a, m.batch, h->s0);
+  a.k_from_row = 1; a.k_end = static_cast<int>(np); a.epi = 0;
+  launch_dmma_gemm(m.mapA.m128, m.mapA.m128, a, m.batch, h->s0, 128);
   ++h->launches;
 }
 
@@ -286,7 +286,7 @@ int gpr_nlml_grad_chunk(gpb_handle* h, const double* khyp, int64_t B, double mea
     GPB_CUDA(cudaMemsetAsync(m.info, 0, static_cast<size_t>(bc) * 4, h->s0));
     finalize_factor_mat(m);
     // one tensor map over all rows of the buffer serves both sweeps and the U U^T product
-    make_tensor_map(&m.mapA, m.A, np, rows_alloc, bc, np, m.batch_stride);
+    make_tile_maps(&m.mapA, m.A, np, rows_alloc, bc, np, m.batch_stride);
 
     h->XsT.ensure(static_cast<size_t>(chunk) * d * np * 8);
     h->sq.ensure(static_cast<size_t>(chunk) * np * 8);

@@ -165,7 +165,7 @@ FactorMat laplace_mat(gpb_handle* h, int64_t rows_total) {
   h->info.ensure(64);
   m.info = h->info.as<int>();
   finalize_factor_mat(m);
-  make_tensor_map(&m.mapA, m.A, np, rows_alloc, 1, np, m.batch_stride);
+  make_tile_maps(&m.mapA, m.A, np, rows_alloc, 1, np, m.batch_stride);
   return m;
 }
 
