@@ -221,9 +221,11 @@ const char* gpb_last_error(gpb_handle* h) { return h ? h->err.c_str() : g_create
 int gpb_set_option(gpb_handle* h, const char* name, int64_t value) {
   if (!h || !name) return -1;
   if (!strcmp(name, "lookahead")) h->lookahead = value != 0;
-  else if (!strcmp(name, "nb_tiles")) h->nb_tiles = static_cast<int>(value < 1 ? 1 : (value > 8 ? 8 : value));
+  else if (!strcmp(name, "nb_tiles")) h->nb_tiles = static_cast<int>(value < 0 ? 0 : (value > 8 ? 8 : value));
   else if (!strcmp(name, "batch_chunk")) h->batch_chunk = value;
   else if (!strcmp(name, "small_tile_threshold")) h->small_tile_threshold = value;
+  else if (!strcmp(name, "split_tiles")) h->split_tiles = value != 0;
+  else if (!strcmp(name, "persistent_waves")) dmma_gemm_set_persistent(static_cast<int>(value));
   else { h->err = std::string("unknown option ") + name; return -1; }
   return 0;
 }
@@ -455,15 +457,17 @@ int gpb_dgemm_nt_dev(gpb_handle* h, double* C, int64_t ldc, const double* A, int
   int epi;
   if (alpha == 1.0 && beta == 0.0) epi = 0;
   else if (alpha == -1.0 && beta == 1.0) epi = 1;
+  else if (alpha == 0.0 && beta == 0.0) epi = 2;      // measurement only: k loop without the epilogue stores
   else throw Error{"dgemm_nt_dev supports (alpha,beta) = (1,0) or (-1,1)"};
-  CUtensorMap ma, mb;
-  make_tensor_map(&ma, A, K, M, 1, lda, M * lda);
-  make_tensor_map(&mb, B, K, N, 1, ldb, N * ldb);
+  TileMaps ma, mb;
+  make_tile_maps(&ma, A, K, M, 1, lda, M * lda);
+  make_tile_maps(&mb, B, K, N, 1, ldb, N * ldb);
   GemmArgs a{};
   a.C = C; a.ldc = ldc; a.c_batch_stride = 0; a.rows_total = static_cast<int>(M);
   a.j0 = 0; a.j1 = static_cast<int>(N / TILE); a.R = static_cast<int>(M / TILE); a.tri = 0; a.i0 = 0;
   a.ka0 = 0; a.kb0 = 0; a.nk = static_cast<int>(K / GEMM_KB); a.b_row0 = 0; a.epi = epi;
-  launch_dmma_gemm(ma, mb, a, 1, h->s0, 128);
+  if (h->split_tiles) launch_dmma_gemm(ma.m128, mb.m64, a, 1, h->s0, 12864);
+  else launch_dmma_gemm(ma.m128, mb.m128, a, 1, h->s0, 128);
   ++h->launches;
   GPB_API_END
 }

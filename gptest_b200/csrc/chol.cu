@@ -112,6 +112,8 @@ struct Sweep {
     if (n128 <= 0) return;
     if (static_cast<int64_t>(n128) * m.batch < h->small_tile_threshold) {
       launch_dmma_gemm(ma.m64, mb.m64, gemm_args_to_64(a), m.batch, st, 64);
+    } else if (h->split_tiles) {
+      launch_dmma_gemm(ma.m128, mb.m64, a, m.batch, st, 12864);
     } else {
       launch_dmma_gemm(ma.m128, mb.m128, a, m.batch, st, 128);
     }
@@ -181,7 +183,10 @@ void chol_sweep(gpb_handle* h, FactorMat& m, const SweepPlan& plan) {
   s.x0 = plan.extra_tile0 >= 0 ? plan.extra_tile0 : nt;
   s.xn = plan.extra_tiles > 0 ? plan.extra_tiles : R - s.x0;
   s.grow = plan.grow;
-  const int nb = h->nb_tiles < 1 ? 1 : h->nb_tiles;
+  // outer block width: wide blocks amortise the per-tile turnover of the trailing update (K = 128 nb),
+  // narrow ones keep the panel short where it cannot be hidden (measured: profiles/r01_tune_potrf.json)
+  int nb = h->nb_tiles;
+  if (nb < 1) nb = (m.batch > 1) ? 2 : (nt >= 96 ? 4 : (nt >= 48 ? 2 : 1));
   // without a symmetric part to factor there is no panel critical path: plain order
   const bool la = h->lookahead && factor && m.batch == 1 && nt > nb;
 

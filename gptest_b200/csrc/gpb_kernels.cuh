@@ -24,7 +24,8 @@ struct GemmArgs {
   // upper triangular: U U^T products), i.e. ka0 = kb0 = T it and nk = (k_end - T it) / 16.
   int ka0, kb0, nk, a_row0, b_row0, k_from_row, k_end;
   int epi;                  // 0: C = acc     1: C = C - acc
-  int ntiles;               // gridDim.x
+  int ntiles;               // region tiles per batch entry (filled by the launcher)
+  int nbatch;               // batch entries (filled by the launcher); work list = nbatch x tiles
 };
 int gemm_region_tiles(const GemmArgs& a);       // host: number of tiles of the region
 // one tensor map per tile edge: the TMA box height is part of the map
@@ -37,6 +38,7 @@ void launch_dmma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmArgs
 // region given in 128-tile units -> the same region in 64-tile units
 GemmArgs gemm_args_to_64(const GemmArgs& a);
 void dmma_gemm_init();                           // sets the dynamic smem attribute once
+void dmma_gemm_set_persistent(int waves);        // 0 (default): one CTA per tile; n: persistent grid of n waves
 
 // ---------------------------------------------------------------------------------------
 // Diagonal-tile factorisation: L = chol(A_kk) in place (lower), W = L^-1 to Dinv[k] (dense

@@ -223,7 +223,8 @@ void chol_inverse_lower(gpb_handle* h, FactorMat& m) {
   a.j0 = 0; a.j1 = nt; a.R = nt; a.tri = 1; a.i_off = 0;
   a.a_row0 = a.b_row0 = static_cast<int>(np + TILE);
   a.k_from_row = 1; a.k_end = static_cast<int>(np); a.epi = 0;
-  launch_dmma_gemm(m.mapA.m128, m.mapA.m128, a, m.batch, h->s0, 128);
+  if (h->split_tiles) launch_dmma_gemm(m.mapA.m128, m.mapA.m64, a, m.batch, h->s0, 12864);
+  else launch_dmma_gemm(m.mapA.m128, m.mapA.m128, a, m.batch, h->s0, 128);
   ++h->launches;
 }
 

@@ -114,33 +114,61 @@ __global__ void __launch_bounds__(256) scale_copy_lower_kernel(const double* __r
 __global__ void __launch_bounds__(256) trsv_lt_step_kernel(const double* __restrict__ L, int64_t ld,
                                                            const double* __restrict__ Dinv, int k,
                                                            double* __restrict__ r, double* __restrict__ x) {
+  // written for memory-level parallelism: every load below is independent of the running sums
   __shared__ double rk[TILE];
   __shared__ double xk[TILE];
+  __shared__ double part[256];
   const int t = threadIdx.x;
   if (t < TILE) rk[t] = r[k * TILE + t];
   __syncthreads();
+  {
+    // x_k = W_k^T r_k on all 256 threads: column c, row half h (rows above the diagonal of W hold zeros)
+    const int c = t & 127, h = t >> 7;
+    const double* W = Dinv + static_cast<int64_t>(k) * TILE * TILE + c;
+    double acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 64; i += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int row = 64 * h + i + u;
+        acc[u] = fma(W[row * TILE], rk[row], acc[u]);
+      }
+    }
+    part[t] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  }
+  __syncthreads();
   if (t < TILE) {
-    const double* W = Dinv + static_cast<int64_t>(k) * TILE * TILE;
-    double s = 0.0;
-    for (int row = t; row < TILE; ++row) s = fma(W[row * TILE + t], rk[row], s);   // W lower: rows >= column
+    const double s = part[t] + part[t + 128];
     xk[t] = s;
     if (blockIdx.x == 0) x[k * TILE + t] = s;
   }
   __syncthreads();
-  const int64_t c = static_cast<int64_t>(blockIdx.x) * 256 + t;
-  if (c < static_cast<int64_t>(k) * TILE) {
-    const double* Lk = L + static_cast<int64_t>(k) * TILE * ld + c;
-    double s = 0.0;
-#pragma unroll 8
-    for (int row = 0; row < TILE; ++row) s = fma(Lk[row * ld], xk[row], s);
-    r[c] -= s;
+  // r_c -= L[tile k rows][c] . x_k for 64 columns per CTA, the 128 rows cut into 4 quarters
+  const int cl = t & 63, q = t >> 6;
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * 64 + cl;
+  const bool on = c < static_cast<int64_t>(k) * TILE;
+  double s = 0.0;
+  if (on) {
+    const double* Lk = L + (static_cast<int64_t>(k) * TILE + 32 * q) * ld + c;
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = fma(Lk[(i + u) * ld], xk[32 * q + i + u], a[u]);
+    }
+    s = (a[0] + a[1]) + (a[2] + a[3]);
   }
+  part[t] = s;
+  __syncthreads();
+  if (q == 0 && on) r[c] -= (part[cl] + part[cl + 64]) + (part[cl + 128] + part[cl + 192]);
 }
 
 void trsv_lt(gpb_handle* h, const FactorMat& m, double* r, double* x) {
   const int nt = static_cast<int>(m.n_pad / TILE);
   for (int k = nt - 1; k >= 0; --k) {
-    const int blocks = k == 0 ? 1 : (k * TILE + 255) / 256;
+    const int blocks = k == 0 ? 1 : 2 * k;
     trsv_lt_step_kernel<<<blocks, 256, 0, h->s0>>>(m.A, m.ld, m.Dinv, k, r, x);
     GPB_CUDA(cudaGetLastError());
     ++h->launches;
