@@ -13,6 +13,13 @@
 // staged d-major in shared memory (conflict-free column reads, broadcast row reads).  In the
 // symmetric mode only tiles on or below the diagonal are computed; the mirror tile is written
 // through a padded shared-memory transpose so both writes are full-line coalesced.
+//
+// The kernel is a pure write stream (2 GiB at N=16384; a plain fill reaches 7.4 TB/s on this part), so
+// what has to be kept small is the instruction count per element: ncu on the first version showed 179
+// thread instructions per computed element (55 FP64 - 37 in the library exp -, 23 IMAD, 15 FSEL).
+// Hence: table-driven exp (gpb_exp.cuh, 11 FP64), mode / clip as template parameters, row pointers
+// hoisted, padding selects only in edge tiles.
+#include "gpb_exp.cuh"
 #include "gpb_kernels.cuh"
 
 namespace gpb {
@@ -46,16 +53,20 @@ void launch_se_prep(const double* X, int64_t n, int d, const double* ell_dev, do
   GPB_CUDA(cudaGetLastError());
 }
 
-__global__ void __launch_bounds__(256) se_build_kernel(const SeArgs p) {
+// MODE 0: symmetric, both triangles  1: symmetric, lower tiles only  2: rectangular  3: rectangular, raw r^2
+template <int MODE, int CLIP>
+__global__ void __launch_bounds__(256, 4) se_build_kernel(const SeArgs p) {
   __shared__ double xr[SDC][ST];
   __shared__ double xc[SDC][ST];
   __shared__ double tt[ST][ST + 1];
+  __shared__ double etab[64];
   const int t = threadIdx.x;
   const int tx = t & 15, ty = t >> 4;
   const int b = blockIdx.y;
+  exp_table_to_smem(etab);                      // made visible by the barriers of the staging loop below
 
   int64_t ti, tj;
-  if (p.mode >= 2) {
+  if (MODE >= 2) {
     const int64_t ntc = p.cols_pad / ST;
     ti = blockIdx.x / ntc;
     tj = blockIdx.x % ntc;
@@ -101,41 +112,70 @@ __global__ void __launch_bounds__(256) se_build_kernel(const SeArgs p) {
   const double sf2 = p.hyp_dev[2 * b], sn2 = p.hyp_dev[2 * b + 1];
   const double* rsq = p.r_sq + b * p.sq_batch_stride;
   const double* csq = p.c_sq + b * p.sq_batch_stride;
-  double sr[4], sc[4];
+  // -r2/2 = ab - (|a|^2/2 + |b|^2/2): the halvings are exact, so this is bit-identical to
+  // -0.5 * ((A2 + B2) - 2 AB) of GPr.py:12,102 with one operation less per element
+  double hr[4], hc[4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a) sr[a] = rsq[i0 + ty + 16 * a];
+  for (int a = 0; a < 4; ++a) hr[a] = 0.5 * rsq[i0 + ty + 16 * a];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) sc[c] = csq[j0 + tx + 16 * c];
+  for (int c = 0; c < 4; ++c) hc[c] = 0.5 * csq[j0 + tx + 16 * c];
 
+  // one pointer per owned row, element (a, c) at rowp[a] + 16 c: no per-element address arithmetic
   double* out = p.out + b * p.out_batch_stride;
-  const bool mirror = (p.mode == 0) && (ti != tj);
+  double* rowp[4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int64_t r = i0 + ty + 16 * a;
+  for (int a = 0; a < 4; ++a) rowp[a] = out + (i0 + ty + 16 * a) * p.ld + j0 + tx;
+  const bool mirror = (MODE == 0) && (ti != tj);
+  const bool interior = (i0 + ST <= p.n_rows_valid) && (j0 + ST <= p.n_cols_valid);
+  const bool diag_tile = (MODE < 2) && (ti == tj);
+
+  double val[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const int64_t cc = j0 + tx + 16 * c;
-      double r2 = (sr[a] + sc[c]) - 2.0 * dot[a][c];          // GPr.py:12  A2 + B2 - AB
-      if (p.clip) r2 = fmax(r2, 0.0);
-      double val = (p.mode == 3) ? r2 : sf2 * exp(-0.5 * r2);   // GPr.py:102 / :109 (mode 3: GPr.py:12 only)
-      if (p.mode < 2) {
-        if (r == cc) val += sn2;                              // sn2 * eye
-        if (r >= p.n_rows_valid || cc >= p.n_cols_valid) val = (r == cc) ? 1.0 : 0.0;   // identity padding
-      } else if (r >= p.n_rows_valid || cc >= p.n_cols_valid) {
-        val = 0.0;
-      }
-      out[r * p.ld + cc] = val;
-      if (mirror) tt[ty + 16 * a][tx + 16 * c] = val;
+      double x = dot[a][c] - (hr[a] + hc[c]);
+      if (CLIP) x = fmin(x, 0.0);                                    // r2 clipped at 0 (GPy RBF semantics)
+      val[a][c] = (MODE == 3) ? -2.0 * x : sf2 * exp_tab(x, etab);   // GPr.py:102 / :109 (mode 3: GPr.py:12 only)
     }
+  if (diag_tile && ty == tx) {                                 // sn2 * eye: cells with a == c of the threads on the diagonal
+#pragma unroll
+    for (int a = 0; a < 4; ++a) val[a][a] += sn2;
   }
-  if (mirror) {
-    __syncthreads();
+  if (!interior) {                                             // edge tiles only: identity (symmetric) / zero (rectangular) padding
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        out[(j0 + ty + 16 * a) * p.ld + i0 + tx + 16 * c] = tt[tx + 16 * c][ty + 16 * a];
+      for (int c = 0; c < 4; ++c) {
+        const int64_t r = i0 + ty + 16 * a, cc = j0 + tx + 16 * c;
+        if (r >= p.n_rows_valid || cc >= p.n_cols_valid) val[a][c] = (MODE < 2 && r == cc) ? 1.0 : 0.0;
+      }
   }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) rowp[a][16 * c] = val[a][c];
+  if (mirror) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tt[ty + 16 * a][tx + 16 * c] = val[a][c];
+    __syncthreads();
+    double* mp = out + (j0 + ty) * p.ld + i0 + tx;
+    const int64_t rstep = 16 * p.ld;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) mp[16 * c] = tt[tx + 16 * c][ty + 16 * a];
+      mp += rstep;
+    }
+  }
+}
+
+template <int MODE>
+static void launch_mode(const SeArgs& a, dim3 grid, cudaStream_t st) {
+  if (a.clip) se_build_kernel<MODE, 1><<<grid, 256, 0, st>>>(a);
+  else se_build_kernel<MODE, 0><<<grid, 256, 0, st>>>(a);
 }
 
 void launch_se_build(const SeArgs& a, int batch, cudaStream_t st) {
@@ -144,7 +184,12 @@ void launch_se_build(const SeArgs& a, int batch, cudaStream_t st) {
   int64_t tiles = (a.mode >= 2) ? tr * tcn : tr * (tr + 1) / 2;
   if (tiles == 0) return;
   dim3 grid(static_cast<unsigned>(tiles), batch);
-  se_build_kernel<<<grid, 256, 0, st>>>(a);
+  switch (a.mode) {
+    case 0: launch_mode<0>(a, grid, st); break;
+    case 1: launch_mode<1>(a, grid, st); break;
+    case 2: launch_mode<2>(a, grid, st); break;
+    default: launch_mode<3>(a, grid, st); break;
+  }
   GPB_CUDA(cudaGetLastError());
 }
 
