@@ -29,7 +29,7 @@ extern "C" int gpb_gpr_nlml_batched(gpb_handle* h, const double* khyp, int64_t B
     // problems resident at once: bounded by memory (A + Dinv per problem) and by option
     size_t free_b = 0, total_b = 0;
     GPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t per_problem = static_cast<size_t>(np + 1) * np * 8 + static_cast<size_t>(np) * TILE * 8 +
+    const size_t per_problem = static_cast<size_t>(np) * np * 8 + static_cast<size_t>(np) * TILE * 8 +
                                static_cast<size_t>(d + 2) * np * 8;
     int64_t chunk = h->batch_chunk > 0 ? h->batch_chunk : 256;
     const size_t budget = (free_b + h->A.bytes + h->Dinv.bytes) / 2;      // leave half of the free memory alone
@@ -57,8 +57,8 @@ extern "C" int gpb_gpr_nlml_batched(gpb_handle* h, const double* khyp, int64_t B
       const double* hyp2 = ell + static_cast<size_t>(bc) * d;
 
       FactorMat m;
-      m.ld = np; m.n_pad = np; m.rows_total = np + 1; m.batch = bc;
-      m.batch_stride = (np + 1) * np;
+      m.ld = np; m.n_pad = np; m.rows_total = np; m.batch = bc;     // no appended row: see launch_trsv_l below
+      m.batch_stride = np * np;
       h->A.ensure(static_cast<size_t>(chunk) * m.batch_stride * 8);
       m.A = h->A.as<double>();
       m.dinv_bs = np * TILE;
@@ -84,10 +84,16 @@ extern "C" int gpb_gpr_nlml_batched(gpb_handle* h, const double* khyp, int64_t B
       a.d = d; a.out = m.A; a.ld = np; a.out_batch_stride = m.batch_stride;
       a.rows_pad = a.cols_pad = np; a.hyp_dev = hyp2; a.mode = 1; a.clip = 0;
       launch_se_build(a, bc, h->s0);
-      launch_set_y_rows(m.A, m.batch_stride, np * np, h->y.as<double>(), h->n, np, mean, bc, h->s0);
+      // right-hand sides: r = y - mean per problem (scratch), z = L^-1 r
+      h->aux0.ensure(static_cast<size_t>(chunk) * np * 8 * 2);
+      double* rv = h->aux0.as<double>();
+      double* zv = rv + static_cast<size_t>(chunk) * np;
+      launch_set_y_rows(rv, np, 0, h->y.as<double>(), h->n, np, mean, bc, h->s0);
       h->launches += 3;
       chol_sweep(h, m, true);
-      launch_nlml_finish(m.A + np * np, m.batch_stride, m.diag, m.diag_bs, np, h->n, h->scal.as<double>(), bc, h->s0);
+      launch_trsv_l(m.A, m.ld, m.batch_stride, m.Dinv, m.dinv_bs, np, rv, np, zv, np, bc, h->s0);
+      h->launches += static_cast<int>(np / TILE);
+      launch_nlml_finish(zv, np, m.diag, m.diag_bs, np, h->n, h->scal.as<double>(), bc, h->s0);
       ++h->launches;
       double* hres = host + cnt;
       int* hinfo = reinterpret_cast<int*>(hres + bc);
