@@ -27,16 +27,20 @@ extern "C" int gpb_gpr_nlml_batched(gpb_handle* h, const double* khyp, int64_t B
     const int64_t np = h->n_pad;
     const int d = h->d;
     // problems resident at once: bounded by memory (A + Dinv per problem) and by option
-    size_t free_b = 0, total_b = 0;
-    GPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const size_t per_problem = static_cast<size_t>(np) * np * 8 + static_cast<size_t>(np) * TILE * 8 +
                                static_cast<size_t>(d + 2) * np * 8;
     int64_t chunk = h->batch_chunk > 0 ? h->batch_chunk : 256;
-    const size_t budget = (free_b + h->A.bytes + h->Dinv.bytes) / 2;      // leave half of the free memory alone
-    if (static_cast<size_t>(chunk) * per_problem > budget) chunk = static_cast<int64_t>(budget / per_problem);
-    if (chunk < 1) chunk = 1;
     if (chunk > B) chunk = B;
     if (chunk > 65535) chunk = 65535;
+    if (static_cast<size_t>(chunk) * np * np * 8 > h->A.bytes) {
+      // the work space has to grow: only then ask the driver how much room there is (the query is slow
+      // and erratic on a shared host - it showed up as 10-30 ms of jitter per call)
+      size_t free_b = 0, total_b = 0;
+      GPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      const size_t budget = (free_b + h->A.bytes + h->Dinv.bytes) / 2;    // leave half of the free memory alone
+      if (static_cast<size_t>(chunk) * per_problem > budget) chunk = static_cast<int64_t>(budget / per_problem);
+      if (chunk < 1) chunk = 1;
+    }
 
     h->scal.ensure(static_cast<size_t>(chunk) * 8 < 64 ? 64 : static_cast<size_t>(chunk) * 8);
     GPB_CUDA(cudaEventRecord(h->tev[0], h->s0));

@@ -15,6 +15,7 @@
 // Reductions are fixed-order (per-CTA partials, then one CTA): results are run-to-run identical.
 #include "../../include/gpb200.h"
 #include "gpb_context.cuh"
+#include "gpb_exp.cuh"
 
 namespace gpb {
 
@@ -77,8 +78,10 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const TraceArgs p) {
   __shared__ double xr[GDC][GT];
   __shared__ double xc[GDC][GT];
   __shared__ double red[256];
+  __shared__ double etab[64];
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
   const int b = blockIdx.y;
+  exp_table_to_smem(etab);                       // visible after the barriers of the staging loop
   int64_t ti = static_cast<int64_t>((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
   while ((ti + 1) * (ti + 2) / 2 <= blockIdx.x) ++ti;
   while (ti * (ti + 1) / 2 > blockIdx.x) --ti;
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const TraceArgs p) {
       double v = 0.0;
       if (r < p.n && cc < p.n) {
         const double r2 = (sq[r] + sq[cc]) - 2.0 * dot[a][c];
-        const double kse = sf2 * exp(-0.5 * r2);
+        const double kse = sf2 * exp_tab(-0.5 * r2, etab);     // same exp as the assembly kernel
         const double Q = Kinv[r * p.ld + cc] - al[r] * al[cc];
         v = wgt * Q * kse;
         if (r == cc) acc_sn += Q;
@@ -243,17 +246,20 @@ int gpr_nlml_grad_chunk(gpb_handle* h, const double* khyp, int64_t B, double mea
   GPB_REQUIRE(P <= GMAXP + 1000, "too many dimensions");
   const int nt = static_cast<int>(np / TILE);
   const int64_t rows_alloc = 2 * np + TILE;
-  size_t free_b = 0, total_b = 0;
-  GPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
   const int64_t t64 = np / GT;
   const int64_t ntiles = t64 * (t64 + 1) / 2;
   const size_t per_problem = static_cast<size_t>(rows_alloc) * np * 8 + static_cast<size_t>(np) * TILE * 8 +
                              static_cast<size_t>(d + 4) * np * 8 + static_cast<size_t>(ntiles) * P * 8;
   int64_t chunk = h->batch_chunk > 0 ? h->batch_chunk : 64;
-  const size_t budget = (free_b + h->A.bytes + h->Dinv.bytes + h->aux0.bytes) / 2;
-  if (static_cast<size_t>(chunk) * per_problem > budget) chunk = static_cast<int64_t>(budget / per_problem);
-  if (chunk < 1) chunk = 1;
   if (chunk > B) chunk = B;
+  if (static_cast<size_t>(chunk) * rows_alloc * np * 8 > h->A.bytes) {
+    // only when the work space must grow (cudaMemGetInfo is slow and erratic on a shared host)
+    size_t free_b = 0, total_b = 0;
+    GPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = (free_b + h->A.bytes + h->Dinv.bytes + h->aux0.bytes) / 2;
+    if (static_cast<size_t>(chunk) * per_problem > budget) chunk = static_cast<int64_t>(budget / per_problem);
+    if (chunk < 1) chunk = 1;
+  }
 
   GPB_CUDA(cudaEventRecord(h->tev[0], h->s0));
   for (int64_t b0 = 0; b0 < B; b0 += chunk) {
