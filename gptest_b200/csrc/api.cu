@@ -226,6 +226,9 @@ int gpb_set_option(gpb_handle* h, const char* name, int64_t value) {
   else if (!strcmp(name, "small_tile_threshold")) h->small_tile_threshold = value;
   else if (!strcmp(name, "split_tiles")) h->split_tiles = value != 0;
   else if (!strcmp(name, "persistent_waves")) dmma_gemm_set_persistent(static_cast<int>(value));
+  else if (!strcmp(name, "stagger")) dmma_gemm_set_stagger(static_cast<int>(value));
+  else if (!strcmp(name, "nb_switch4")) h->nb_switch4 = static_cast<int>(value);
+  else if (!strcmp(name, "nb_switch2")) h->nb_switch2 = static_cast<int>(value);
   else { h->err = std::string("unknown option ") + name; return -1; }
   return 0;
 }

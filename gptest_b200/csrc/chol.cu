@@ -184,26 +184,35 @@ void chol_sweep(gpb_handle* h, FactorMat& m, const SweepPlan& plan) {
   s.xn = plan.extra_tiles > 0 ? plan.extra_tiles : R - s.x0;
   s.grow = plan.grow;
   // outer block width: wide blocks amortise the per-tile turnover of the trailing update (K = 128 nb),
-  // narrow ones keep the panel short where it cannot be hidden (measured: profiles/r01_tune_potrf.json)
-  int nb = h->nb_tiles;
-  if (nb < 1) nb = (m.batch > 1) ? 2 : (nt >= 96 ? 4 : (nt >= 48 ? 2 : 1));
+  // narrow ones keep the panel short where it cannot be hidden (measured: profiles/r01_tune_potrf.json).
+  // With nb_tiles == 0 the width follows the REMAINING matrix: 4 tiles while the trailing update is long
+  // enough to hide a 4-tile panel, then 2, then 1 in the panel-bound tail.
+  auto width_at = [&](int kb) {
+    if (h->nb_tiles > 0) return h->nb_tiles;
+    if (m.batch > 1) return 2;
+    const int rem = nt - kb;
+    return rem >= h->nb_switch4 ? 4 : (rem >= h->nb_switch2 ? 2 : 1);
+  };
   // without a symmetric part to factor there is no panel critical path: plain order
-  const bool la = h->lookahead && factor && m.batch == 1 && nt > nb;
+  const bool la = h->lookahead && factor && m.batch == 1 && nt > width_at(0);
 
   if (!la) {
-    for (int kb = 0; kb < nt; kb += nb) {
+    for (int kb = 0; kb < nt;) {
+      const int nb = width_at(kb);
       const int kend = kb + nb < nt ? kb + nb : nt;
       s.panel(kb, kend, h->s0);
       s.update(kend, nt, kb, kend, h->s0);
+      kb = kend;
     }
     return;
   }
 
-  s.panel(0, nb < nt ? nb : nt, h->s0);
-  for (int kb = 0; kb < nt; kb += nb) {
-    const int kend = kb + nb < nt ? kb + nb : nt;
-    if (kend >= nt) break;
-    const int nend = kend + nb < nt ? kend + nb : nt;
+  int kb = 0;
+  int kend = width_at(0) < nt ? width_at(0) : nt;
+  s.panel(0, kend, h->s0);
+  while (kend < nt) {
+    const int nbn = width_at(kend);
+    const int nend = kend + nbn < nt ? kend + nbn : nt;
     s.update(kend, nend, kb, kend, h->s0);            // columns of the next panel first
     cudaEvent_t eu = h->next_event();
     GPB_CUDA(cudaEventRecord(eu, h->s0));
@@ -213,6 +222,8 @@ void chol_sweep(gpb_handle* h, FactorMat& m, const SweepPlan& plan) {
     GPB_CUDA(cudaEventRecord(ep, h->s1));
     s.update(nend, nt, kb, kend, h->s0);               // ... while the rest of the update runs
     GPB_CUDA(cudaStreamWaitEvent(h->s0, ep, 0));
+    kb = kend;
+    kend = nend;
   }
 }
 

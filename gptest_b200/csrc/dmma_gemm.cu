@@ -73,6 +73,15 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const int per_batch = p.ntiles * NSPLIT;   // CTA-tiles per batch entry
   const int total = per_batch * p.nbatch;    // work items of this launch: (batch entry, CTA-tile)
 
+  // CTAs that share an SM start together and then run in lockstep - both in their prologue, both in their
+  // epilogue at the same time, so nothing overlaps.  The second resident CTA of every SM (first wave only)
+  // waits half a tile time; the pair then stays out of phase for the rest of the launch.
+  if (MINB >= 2 && p.stagger_clk > 0 && blockIdx.x >= static_cast<unsigned>(p.num_sms) &&
+      blockIdx.x < 2u * static_cast<unsigned>(p.num_sms)) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < p.stagger_clk) __nanosleep(2000);
+  }
+
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < GEMM_STAGES; ++s) {
@@ -254,6 +263,8 @@ constexpr int smem_bytes(int bm, int bn) { return GEMM_STAGES * (bm + bn) * GEMM
 static int g_num_sms = 148;
 static int g_persistent_waves = 0;
 void dmma_gemm_set_persistent(int waves) { g_persistent_waves = waves < 0 ? 0 : waves; }
+static int g_stagger = 1;
+void dmma_gemm_set_stagger(int on) { g_stagger = on != 0; }
 
 void dmma_gemm_init() {
   GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<128, 128, 2, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -281,6 +292,12 @@ void launch_dmma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmArgs
   // caps the grid at that many resident waves instead (CTAs then walk the list with a grid stride
   // and prefetch across tile boundaries; measured: +3 % at K=512, -5 % at K=8192, look-ahead starved).
   a.nbatch = batch < 1 ? 1 : batch;
+  a.num_sms = g_num_sms;
+  {
+    // half of the time a CTA-tile takes when two CTAs share the FP64 tensor pipe: nk slabs x 2048 clocks
+    const long long nk = a.k_from_row ? (a.k_end / GEMM_KB) / 2 : a.nk;
+    a.stagger_clk = (g_stagger && static_cast<int64_t>(ntiles) * a.nbatch >= 2LL * g_num_sms) ? nk * 2048 : 0;
+  }
   auto grid_for = [&](int cta_tiles, int per_sm) {
     const int64_t work = static_cast<int64_t>(cta_tiles) * a.nbatch;
     int64_t gx = work;

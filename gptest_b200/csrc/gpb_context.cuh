@@ -54,11 +54,12 @@ struct gpb_handle {
 
   // options
   int lookahead = 1;
-  int nb_tiles = 0;              // 0 = choose from the matrix size
+  int nb_tiles = 0;              // 0 = choose from the remaining matrix size (see chol.cu)
+  int nb_switch4 = 64, nb_switch2 = 24;   // remaining tile columns from which the block is 4 / 2 tiles wide
   int64_t batch_chunk = 0;       // 0 = auto
   int split_tiles = 1;           // big launches: 1 = 128x64 CTAs, two per SM (finer grain: the look-ahead panel
                                  // kernels get SMs sooner, N=16384: 49.7 vs 52.4 ms); 0 = 128x128, one per SM
-  int64_t small_tile_threshold = 296;   // launches with fewer 128-tiles than this use 64-tiles
+  int64_t small_tile_threshold = 2400;  // launches with fewer 128-tiles than this use 64-tiles (tuned: r01_tune_potrf.json)
 
   // training data (GPr.py:25-26 keeps trainInput / trainTarget on the object)
   int64_t n = 0, n_pad = 0;

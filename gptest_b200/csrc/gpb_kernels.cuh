@@ -26,6 +26,8 @@ struct GemmArgs {
   int epi;                  // 0: C = acc     1: C = C - acc
   int ntiles;               // region tiles per batch entry (filled by the launcher)
   int nbatch;               // batch entries (filled by the launcher); work list = nbatch x tiles
+  int num_sms;              // filled by the launcher
+  long long stagger_clk;    // > 0: delay (SM clocks) of the second resident CTA per SM in the first wave
 };
 int gemm_region_tiles(const GemmArgs& a);       // host: number of tiles of the region
 // one tensor map per tile edge: the TMA box height is part of the map
@@ -39,6 +41,7 @@ void launch_dmma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmArgs
 GemmArgs gemm_args_to_64(const GemmArgs& a);
 void dmma_gemm_init();                           // sets the dynamic smem attribute once
 void dmma_gemm_set_persistent(int waves);        // 0 (default): one CTA per tile; n: persistent grid of n waves
+void dmma_gemm_set_stagger(int on);              // 1 (default): phase-shift co-resident CTAs of the 2-per-SM variants
 
 // ---------------------------------------------------------------------------------------
 // Diagonal-tile factorisation: L = chol(A_kk) in place (lower), W = L^-1 to Dinv[k] (dense

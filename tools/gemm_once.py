@@ -9,6 +9,8 @@ M, N, K, epi = (int(a) for a in (sys.argv[1:5] + ['8192', '8192', '512', '1'][le
 h = _lib.Handle(0)
 if len(sys.argv) > 5:
     h.set_option('split_tiles', int(sys.argv[5]))
+if len(sys.argv) > 6:
+    h.set_option('stagger', int(sys.argv[6]))
 A = torch.randn(M, K, dtype=torch.float64, device='cuda')
 B = torch.randn(N, K, dtype=torch.float64, device='cuda')
 C = torch.randn(M, N, dtype=torch.float64, device='cuda')
