@@ -86,8 +86,8 @@ def test_pref_laplace_matches_oracle(handle, n, P, D):
     assert np.abs(f - of[:, 0]).max() < 1e-6
     assert abs(lml - olml) <= 1e-8 * abs(olml)
     # opt-in Newton mode converges quadratically to the accumulated-gradient mode
-    nf, nlml, nit, _, _ = handle.pref_laplace(uvi, y, pref_khyp(lh, D), delta_f=1e-9, max_iter=50, grad_mode=1)
-    onf, onlml = gppref_oracle.calc_laplace(x, uvi, y, lh, delta_f=1e-9, max_iter=50, accumulate=True)
+    nf, nlml, nit, _, _ = handle.pref_laplace(uvi, y, pref_khyp(lh, D), delta_f=1e-8, max_iter=50, grad_mode=1)
+    onf, onlml = gppref_oracle.calc_laplace(x, uvi, y, lh, delta_f=1e-8, max_iter=50, accumulate=True)
     assert nit < 15
     assert np.abs(nf - onf[:, 0]).max() < 1e-6
     assert abs(nlml - onlml) <= 1e-8 * abs(onlml)
