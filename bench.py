@@ -157,7 +157,41 @@ def cpu_baseline(budget_s=20.0):
     return {"value": 1.0 / (t * scale), "unit": "fits/s", "cores": blas_threads(), "kind": "port",
             "sample": "one compute_likelihood at N=%d (first %d points of the workload), %.2f s; "
                       "extrapolated x(16384/%d)^3 = %.0f for N=16384" % (ns, ns, t, ns, scale),
-            "host_cpus": os.cpu_count()}
+            "host_cpus": os.cpu_count(), "other_configs": cpu_other_configs()}
+
+
+def cpu_other_configs():
+    """Bounded CPU samples of the oracle ports for configs 5, 4 and 3, a few seconds each."""
+    from oracle import gpr_oracle, gppref_oracle, gpc_oracle
+    out = {}
+    X5, Y5, lhs5 = make_c5()
+    t0 = time.perf_counter()
+    for l in lhs5[:2]:
+        gpr_oracle.nlml(l, X5, Y5)
+    t5 = (time.perf_counter() - t0) / 2
+    out["c5_sweep_1024x2048"] = {"s_per_problem": t5, "ms_extrapolated": t5 * 1024 * 1e3,
+                                 "sample": "2 of the 1024 problems (GPr.py:57-69 port), x512"}
+    rng = np.random.default_rng(0)
+    n, D, P = 1024, 6, 8192
+    x = rng.random((n, D))
+    uvi = rng.integers(0, n, (P, 2))
+    bad = uvi[:, 0] == uvi[:, 1]
+    uvi[bad, 1] = (uvi[bad, 0] + 1) % n
+    y = np.where(rng.random(P) < 0.5, 1.0, -1.0).reshape(-1, 1)
+    t0 = time.perf_counter()
+    gppref_oracle.calc_laplace(x, uvi, y, np.log([0.5] * D + [1.0, 0.1]), max_iter=3)
+    t4 = (time.perf_counter() - t0) / 3
+    out["c4_gppref"] = {"s_per_iteration_n1024": t4, "ms_per_iteration_n4096_extrapolated": t4 * 64 * 1e3,
+                        "sample": "3 iterations of the GPpref.py:112-157 port at n=1024, P=8192; x(4096/1024)^3 per iteration"}
+    n, D = 1024, 4
+    x = rng.random((n, D))
+    yc = np.where(rng.random(n) < 0.5, 1.0, -1.0)
+    t0 = time.perf_counter()
+    f, lml, st = gpc_oracle.calc_laplace(x, yc, np.log([0.5] * D + [1.0]), max_iter=2, return_state=True)
+    t3 = (time.perf_counter() - t0) / max(st["it"], 1)
+    out["c3_gpc"] = {"s_per_newton_step_n1024": t3, "ms_per_newton_step_n8192_extrapolated": t3 * 512 * 1e3,
+                     "sample": "2 Newton steps of the R&W Alg. 3.1 oracle at N=1024; x(8192/1024)^3 per step"}
+    return out
 
 
 def run_reference(args, rank, world):

@@ -2,7 +2,6 @@
 // assembly, regression likelihood / prediction, dense factorisation hooks.
 #include <cmath>
 #include <cstring>
-#include <mutex>
 
 #include "../../include/gpb200.h"
 #include "gpb_context.cuh"
@@ -10,7 +9,6 @@
 using namespace gpb;
 
 static std::string g_create_error;
-static std::once_flag g_init_once;
 
 cudaEvent_t gpb_handle::next_event() {
   if (ev_pool.empty()) {

@@ -12,19 +12,19 @@
 //     (cp.async.bulk.tensor, SASS UTMALDG) with the 128B swizzle through a 4-stage
 //     full/empty mbarrier ring.  The producer duty belongs to the elected lane of warp 0 (registers
 //     are allocated per four warps: a ninth warp would cap the DMMA warps at 168 registers).
-//   * PERSISTENT: the grid is one CTA per SM (times the CTAs that fit); each CTA walks the tile list
-//     with a grid stride and the slab ring runs ACROSS tile boundaries, so the first slabs of the
-//     next tile land while the last slabs of the current tile are multiplied and its epilogue
-//     runs.  Measured before this change: 7-9 us of prologue/turnover per 128x128 tile
-//     (K=512: 87 % of the pipe rate; K=8192: 97 %).
+//   * work list: (batch entry, tile) pairs, walked with a grid stride; the slab ring runs ACROSS tile
+//     boundaries, so a CTA that owns several work items prefetches the next one during the current
+//     epilogue.  By default the grid has one CTA per work item (the hardware scheduler balances SMs
+//     and lets the look-ahead's high-priority panel kernels in between CTAs); a persistent grid is an
+//     option (measured: +3 % at K=512, -5 % at K=8192, look-ahead starved).
 //   * fragment rows are taken with a stride of two tile rows ("parity" fragments): under the
 //     128B swizzle the 16 lanes of a half warp then read 8 distinct 16-byte chunks over 4 rows
 //     = all 32 banks once, so every 64-bit fragment load is conflict free.
-//   * instantiations: 128x128 (8 warps of 64x32, 1 CTA/SM) for throughput - per 16-wide slab a
-//     warp issues 128 DMMA for 48 LDS.64, the FP64 tensor pipe is the only busy unit; 64x64
-//     (4 warps of 32x32, 3 CTAs/SM) for launches on the panel's critical path or too small to
-//     fill 148 SMs; 64x128 for the in-place panel TRSM (a CTA must own all 128 output columns of
-//     its rows); 128x64 (two CTAs per SM) kept as an option.
+//   * instantiations: 128x64 (4 warps of 64x32, two CTAs per SM, second one phase-shifted) for the big
+//     trailing updates - per 16-wide slab a warp issues 128 DMMA for 48 LDS.64, the FP64 tensor pipe
+//     is the only busy unit (92 % active at K=512); 128x128 (8 warps, 1 CTA/SM); 64x64 (4 warps of
+//     32x32, 3 CTAs/SM) for launches on the panel's critical path or too small to fill 148 SMs;
+//     64x128 for the in-place panel TRSM (a CTA must own all 128 output columns of its rows).
 #include "gpb_kernels.cuh"
 
 namespace gpb {

@@ -15,10 +15,6 @@ namespace gpb {
 constexpr int TILE = 128;          // tile edge of the blocked factorisation (elements)
 constexpr int GEMM_KB = 16;        // k-slab per pipeline stage: 16 doubles = one 128-byte TMA row
 constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_CONSUMER_WARPS = 8;
-constexpr int GEMM_THREADS = GEMM_CONSUMER_WARPS * 32;
-constexpr int GEMM_STAGE_BYTES = 2 * TILE * GEMM_KB * 8;       // A slab + B slab = 32 KiB
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 // ---- device-side PTX wrappers ------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

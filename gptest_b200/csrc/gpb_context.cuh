@@ -65,7 +65,7 @@ struct gpb_handle {
   int64_t n = 0, n_pad = 0;
   int d = 0;
   bool has_y = false;
-  gpb::DevBuf X, y, yc;
+  gpb::DevBuf X, y;
 
   // per-call work space
   gpb::DevBuf params;            // ell[d] | sf2, sn2   (per batch entry)

@@ -23,7 +23,6 @@ namespace {
 
 constexpr int GT = 64;       // tile edge of the trace kernel
 constexpr int GDC = 8;       // dimensions per staged chunk
-constexpr int GMAXP = 34;    // up to 32 ARD dimensions + sf + sn
 
 __global__ void set_identity_kernel(double* U, int64_t ld, int64_t n, int64_t batch_stride) {
   double* u = U + blockIdx.y * batch_stride;
@@ -243,7 +242,6 @@ int gpr_nlml_grad_chunk(gpb_handle* h, const double* khyp, int64_t B, double mea
   const int64_t np = h->n_pad;
   const int d = h->d;
   const int P = d + 2;
-  GPB_REQUIRE(P <= GMAXP + 1000, "too many dimensions");
   const int nt = static_cast<int>(np / TILE);
   const int64_t rows_alloc = 2 * np + TILE;
   const int64_t t64 = np / GT;

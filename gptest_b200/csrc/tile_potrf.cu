@@ -17,8 +17,11 @@
 //     step), so the 16 owners of column j know S[j][j] without a broadcast;
 //   * 1/d comes from rsqrt + one Newton correction (no sqrt -> divide chain);
 //   * v is double buffered in shared memory: ONE barrier per column.
-// (Two software-pipelined variants - uniform chain in every warp, and all owners of a column in one
-//  warp - were measured slower: 58.7 and 69.5 us against 53.0 us for this one.)
+// Measured on B200 (tools/micro/lat.cu): a dependent DFMA/DMUL/DADD takes 23 clocks, rsqrt(double) 55, a
+// 256-thread barrier 15 - the chain LDS -> FMA -> rsqrt -> correction -> scale -> STS -> barrier is ~230 clocks
+// per column before any throughput term, and the kernel runs at ~745 clocks per column (50 us per tile).
+// Variants that were measured slower and dropped: two software-pipelined forms (58.7 / 69.5 us), a blocked
+// form with rank-16 updates of the later column blocks (54.5 us: fewer instructions, same chain).
 #include "gpb_kernels.cuh"
 
 namespace gpb {
