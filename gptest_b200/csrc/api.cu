@@ -227,6 +227,7 @@ int gpb_set_option(gpb_handle* h, const char* name, int64_t value) {
   else if (!strcmp(name, "stagger")) dmma_gemm_set_stagger(static_cast<int>(value));
   else if (!strcmp(name, "nb_switch4")) h->nb_switch4 = static_cast<int>(value);
   else if (!strcmp(name, "nb_switch2")) h->nb_switch2 = static_cast<int>(value);
+  else if (!strcmp(name, "la_max_batch")) h->la_max_batch = static_cast<int>(value);
   else { h->err = std::string("unknown option ") + name; return -1; }
   return 0;
 }

@@ -15,6 +15,8 @@
 // Look-ahead: the columns of the next panel are updated first, then the next panel is factored
 // on a high-priority side stream while the main stream updates the rest of the trailing matrix.
 // Both streams are ordered with events only - the host never blocks inside the sweep.
+#include <cmath>
+
 #include "gpb_context.cuh"
 
 namespace gpb {
@@ -189,12 +191,15 @@ void chol_sweep(gpb_handle* h, FactorMat& m, const SweepPlan& plan) {
   // enough to hide a 4-tile panel, then 2, then 1 in the panel-bound tail.
   auto width_at = [&](int kb) {
     if (h->nb_tiles > 0) return h->nb_tiles;
-    if (m.batch > 1) return 2;
-    const int rem = nt - kb;
+    if (m.batch > h->la_max_batch) return 2;
+    // a small batch of big problems: the trailing update holds batch x the tiles, so the panel hides as it
+    // would behind a single matrix sqrt(batch) times larger
+    int rem = nt - kb;
+    if (m.batch > 1) rem = static_cast<int>(rem * sqrt(static_cast<double>(m.batch)));
     return rem >= h->nb_switch4 ? 4 : (rem >= h->nb_switch2 ? 2 : 1);
   };
   // without a symmetric part to factor there is no panel critical path: plain order
-  const bool la = h->lookahead && factor && m.batch == 1 && nt > width_at(0);
+  const bool la = h->lookahead && factor && m.batch <= h->la_max_batch && nt > width_at(0);
 
   if (!la) {
     for (int kb = 0; kb < nt;) {

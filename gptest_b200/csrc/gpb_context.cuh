@@ -57,6 +57,8 @@ struct gpb_handle {
   int nb_tiles = 0;              // 0 = choose from the remaining matrix size (see chol.cu)
   int nb_switch4 = 64, nb_switch2 = 24;   // remaining tile columns from which the block is 4 / 2 tiles wide
   int64_t batch_chunk = 0;       // 0 = auto
+  int la_max_batch = 1 << 30;    // batches up to this size use the look-ahead schedule and adaptive widths
+                                 // (measured: N=16384 B=4 47.5 vs 50.2 ms/fit, N=4096 B=8 1.08 vs 1.20; 1024x2048 neutral)
   int split_tiles = 1;           // big launches: 1 = 128x64 CTAs, two per SM (finer grain: the look-ahead panel
                                  // kernels get SMs sooner, N=16384: 49.7 vs 52.4 ms); 0 = 128x128, one per SM
   int64_t small_tile_threshold = 2400;  // launches with fewer 128-tiles than this use 64-tiles (tuned: r01_tune_potrf.json)

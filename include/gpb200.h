@@ -43,7 +43,10 @@ void* gpb_get_stream(gpb_handle* h);
 int gpb_destroy(gpb_handle* h);
 const char* gpb_last_error(gpb_handle* h);            /* h may be NULL: last create error */
 /* tunables: "lookahead" (0/1), "nb_tiles" (outer block = nb_tiles*128 columns: 1,2,4),
- * "batch_chunk" (problems resident at once in the batched path).  Returns <0 if unknown. */
+ * "batch_chunk" (problems resident at once in the batched path), "la_max_batch" (largest batch that
+ * uses the look-ahead schedule; default: all), and the schedule knobs "nb_switch4", "nb_switch2",
+ * "split_tiles", "small_tile_threshold", "persistent_waves", "stagger" (see gpb_context.cuh).
+ * Returns <0 if unknown. */
 int gpb_set_option(gpb_handle* h, const char* name, int64_t value);
 /* stage times (ms) of the last GPr/potrf call measured with CUDA events on the handle's
  * stream: [0]=covariance assembly [1]=factorisation (+fused forward solves)
