@@ -42,6 +42,10 @@ SIGNATURES = {
     'gpb_gpr_nlml': (C.c_int, [C.c_void_p, c_dp, C.c_double, c_dp, c_dp, c_ip]),
     'gpb_gpr_predict': (C.c_int, [C.c_void_p, c_dp, C.c_double, c_dp, C.c_int64, c_dp, c_dp, c_ip]),
     'gpb_gpr_nlml_batched': (C.c_int, [C.c_void_p, c_dp, C.c_int64, C.c_double, c_dp, c_dp, c_ip]),
+    'gpb_gpr_grow_begin': (C.c_int, [C.c_void_p, c_dp, C.c_int32, C.c_double, C.c_int64]),
+    'gpb_gpr_grow_append': (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int64, c_dp, c_ip]),
+    'gpb_gpr_grow_predict': (C.c_int, [C.c_void_p, c_dp, C.c_int64, c_dp, c_dp]),
+    'gpb_gpr_grow_size': (C.c_int64, [C.c_void_p]),
     'gpb_potrf_lower_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, c_ip]),
     'gpb_potrf_lower': (C.c_int, [C.c_void_p, c_dp, C.c_int64, c_ip]),
     'gpb_dgemm_nt_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
@@ -219,6 +223,35 @@ class Handle:
         self.check(self.lib.gpb_gpr_nlml_batched(self.h, _dp(khyp), B, float(mean), _dp(val),
                                                  _dp(grad) if want_grad else None, info.ctypes.data_as(c_ip)))
         return (val, grad, info) if want_grad else (val, info)
+
+    # ---- growing training set (GP_parameter_fit.py:61-63) --------------------------------------
+    def grow_begin(self, khyp, d, capacity, mean=0.0):
+        khyp = as_f64(khyp).reshape(-1)
+        assert khyp.size == d + 2
+        self.check(self.lib.gpb_gpr_grow_begin(self.h, _dp(khyp), int(d), float(mean), int(capacity)))
+
+    def grow_append(self, X_new, y_new):
+        X_new = as_f64(X_new)
+        X_new = X_new.reshape(len(X_new), -1)
+        y_new = as_f64(y_new).reshape(-1)
+        assert len(X_new) == len(y_new)
+        val = np.empty(1)
+        info = C.c_int32()
+        self.check(self.lib.gpb_gpr_grow_append(self.h, _dp(X_new), _dp(y_new), len(y_new), _dp(val), C.byref(info)))
+        if info.value > 0:
+            raise np.linalg.LinAlgError('Matrix is not positive definite (leading minor %d)' % info.value)
+        return float(val[0])
+
+    def grow_predict(self, Z):
+        Z = as_f64(Z)
+        Z = Z.reshape(len(Z), -1)
+        fz = np.empty(len(Z))
+        cov = np.empty(len(Z))
+        self.check(self.lib.gpb_gpr_grow_predict(self.h, _dp(Z), len(Z), _dp(fz), _dp(cov)))
+        return fz, cov
+
+    def grow_size(self):
+        return int(self.lib.gpb_gpr_grow_size(self.h))
 
     # ---- dense hooks ------------------------------------------------------------------------
     def potrf(self, A):

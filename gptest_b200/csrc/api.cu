@@ -210,6 +210,7 @@ int gpb_destroy(gpb_handle* h) {
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   for (auto e : h->tev) if (e) cudaEventDestroy(e);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  gpb::grow_release(h);
   delete h;
   return 0;
 }

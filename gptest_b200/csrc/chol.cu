@@ -171,6 +171,13 @@ struct Sweep {
 
 }  // namespace
 
+void chol_trailing_update(gpb_handle* h, FactorMat& m, int c0, int c1, int ka, int kb) {
+  const int nt = static_cast<int>(m.n_pad / TILE);
+  const int R = static_cast<int>((m.rows_total + TILE - 1) / TILE);
+  Sweep s{h, m, true, nt, R};
+  s.update(c0, c1, ka, kb, h->s0);
+}
+
 void chol_sweep(gpb_handle* h, FactorMat& m, bool factor) {
   SweepPlan plan;
   plan.factor = factor;

@@ -42,6 +42,8 @@ struct FactorMat {
   TileMaps mapA, mapD;
 };
 
+struct GrowState;    // grow.cu: factor of a growing training set
+
 }  // namespace gpb
 
 struct gpb_handle {
@@ -87,6 +89,8 @@ struct gpb_handle {
   int lap_link = 0;
   std::vector<double> lap_khyp;
 
+  gpb::GrowState* grow = nullptr;     // gpb_gpr_grow_* state (own buffers: other calls do not disturb it)
+
   cudaEvent_t next_event();
   double* pinned(size_t bytes);
 };
@@ -113,6 +117,11 @@ void chol_sweep(gpb_handle* h, FactorMat& m, const SweepPlan& plan);
 // K^-1 on the lower tiles of the symmetric part from its factor (grad.cu); needs the buffer layout
 // rows [0,np) L | [np, np+128) appended tile row | [np+128, 2np+128) scratch for U = L^-T
 void chol_inverse_lower(gpb_handle* h, FactorMat& m);
+
+// A[i,j] -= sum_{k in tile columns [ka,kb)} A[i,k] A[j,k]^T for tile columns j in [c0,c1), rows i >= j (chol.cu)
+void chol_trailing_update(gpb_handle* h, FactorMat& m, int c0, int c1, int ka, int kb);
+
+void grow_release(gpb_handle* h);
 
 // fills m.mapA / m.mapD from the pointers and extents
 void finalize_factor_mat(FactorMat& m);

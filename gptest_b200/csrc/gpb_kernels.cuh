@@ -100,7 +100,7 @@ void launch_row_dot(const double* M, int64_t ld, int64_t m_bs, const double* x, 
                     int64_t ncols, int upper, double* out, int64_t out_bs, int batch, cudaStream_t st);
 // x <- L^-1 r per batch entry by blocked forward substitution with the inverted diagonal tiles (r: scratch)
 void launch_trsv_l(const double* L, int64_t ld, int64_t l_bs, const double* Dinv, int64_t d_bs, int64_t n_pad,
-                   double* r, int64_t r_bs, double* x, int64_t x_bs, int batch, cudaStream_t st);
+                   double* r, int64_t r_bs, double* x, int64_t x_bs, int batch, cudaStream_t st, int k_begin = 0);
 void launch_fill(double* p, int64_t n, double v, cudaStream_t st);
 void launch_copy_sub_mean(double* dst, const double* src, int64_t n, double mean, cudaStream_t st);
 

@@ -147,9 +147,9 @@ __global__ void __launch_bounds__(256) trsv_l_step_kernel(const double* __restri
 }
 // x (n_pad per batch entry) <- L^-1 r for every batch entry; r is used as scratch
 void launch_trsv_l(const double* L, int64_t ld, int64_t l_bs, const double* Dinv, int64_t d_bs, int64_t n_pad,
-                   double* r, int64_t r_bs, double* x, int64_t x_bs, int batch, cudaStream_t st) {
+                   double* r, int64_t r_bs, double* x, int64_t x_bs, int batch, cudaStream_t st, int k_begin) {
   const int nt = static_cast<int>(n_pad / TILE);
-  for (int k = 0; k < nt; ++k) {
+  for (int k = k_begin; k < nt; ++k) {
     const int64_t below = n_pad - static_cast<int64_t>(k + 1) * TILE;
     dim3 grid(static_cast<unsigned>(below > 0 ? (below + 63) / 64 : 1), batch);
     trsv_l_step_kernel<<<grid, 256, 0, st>>>(L, ld, l_bs, Dinv, d_bs, k, n_pad, r, r_bs, x, x_bs);

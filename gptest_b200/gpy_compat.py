@@ -83,6 +83,32 @@ class GPRegression(object):
             self.Y = np.asarray(Y, dtype=float).reshape(len(Y), -1)
         assert self.X.shape[0] == self.Y.shape[0] and self.Y.shape[1] == 1
 
+    def _sync_factor(self):
+        """Bring the factor stored on the device (gpb_gpr_grow_*) in line with (X, Y, parameters).
+
+        The script's replay loop (GP_parameter_fit.py:61-63) calls set_XY with ever longer prefixes and predicts
+        after each: when the data only GREW and the parameters did not change, only the new rows are appended
+        to the factor (O(n^2 m) instead of a refit); otherwise it is rebuilt.  Repeated predictions reuse it."""
+        h = _lib.default_handle()
+        n, d = self.X.shape
+        key = self._theta().tobytes()
+        st = getattr(h, '_grow_state', None)
+        y = self.Y[:, 0]
+        reuse = (st is not None and st['owner'] is self and st['key'] == key and st['n'] <= n <= st['cap']
+                 and h.grow_size() == st['n']
+                 and np.array_equal(st['X'][:st['n']], self.X[:st['n']]) and np.array_equal(st['y'][:st['n']], y[:st['n']]))
+        if not reuse:
+            cap = max(1024, min(2 * n, n + 8192))
+            h.grow_begin(_sweep.natural_params(self._full_log_hyp(self._theta()))[0], d, cap)
+            st = {'owner': self, 'key': key, 'n': 0, 'cap': cap}
+            h._grow_state = st
+        if st['n'] < n:
+            st['n'] = -1                                    # a failing append leaves no reusable state
+            self._last_nlml = h.grow_append(self.X[h.grow_size():n], y[h.grow_size():n])
+            st['n'] = n
+        st['X'], st['y'] = self.X.copy(), y.copy()
+        return h
+
     # ---- parameters: [log lengthscale (1 or D), log sigma_f, log sigma_n] ------------------------------
     def _theta(self):
         return np.concatenate([np.log(np.asarray(self.kern.lengthscale, dtype=float).reshape(-1)),
@@ -175,11 +201,9 @@ class GPRegression(object):
     def predict(self, Xnew, full_cov=False, Y_metadata=None, kern=None, likelihood=None, include_likelihood=True):
         """GP_parameter_fit.py:52 - (mean (M,1), variance (M,1)); the variance includes the noise variance."""
         assert not full_cov, 'full_cov=True is not on the hot path of the reference'
-        h = _lib.default_handle()
-        h.set_train(self.X, self.Y[:, 0])
-        lh = self._full_log_hyp(self._theta())
+        h = self._sync_factor()
         Xnew = np.asarray(Xnew, dtype=float).reshape(len(Xnew), -1)
-        fz, cov = h.gpr_predict(_sweep.natural_params(lh)[0], Xnew)
+        fz, cov = h.grow_predict(Xnew)
         if include_likelihood:
             cov = cov + self.likelihood.variance
         return fz.reshape(-1, 1), cov.reshape(-1, 1)

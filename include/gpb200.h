@@ -93,6 +93,23 @@ int gpb_gpr_predict(gpb_handle* h, const double* khyp, double mean, const double
 int gpb_gpr_nlml_batched(gpb_handle* h, const double* khyp, int64_t B, double mean,
                          double* nlml, double* grad, int32_t* info);
 
+/* ---- growing training sets (GP_parameter_fit.py:61-63,52) ----------------------------------
+ * The reference replays an experiment by calling set_XY on ever longer prefixes (five more points each time)
+ * and predicting on a 100x100 grid - a full refit per step.  With fixed hyper-parameters the factor of the
+ * longer prefix extends the factor of the shorter one, so the handle keeps it on the device:
+ *   gpb_gpr_grow_begin   fixes khyp = [l_1..l_d, sf2, sn2], the mean and the capacity (points); n = 0
+ *   gpb_gpr_grow_append  adds m points (X_new m x d, y_new m; host) and returns the NLML of the enlarged set
+ *                        (what gpb_gpr_nlml returns for it); work O((n+m)^2 m) instead of (n+m)^3/3;
+ *                        info > 0: non-positive pivot at that (1-based) row, the stored factor is then invalid
+ *   gpb_gpr_grow_predict compute_prediction (GPr.py:45-54) from the stored factor, any mz
+ *   gpb_gpr_grow_size    points appended so far (-1 without gpb_gpr_grow_begin)
+ * The state has its own buffers: other calls on the handle do not disturb it. */
+int gpb_gpr_grow_begin(gpb_handle* h, const double* khyp, int32_t d, double mean, int64_t capacity);
+int gpb_gpr_grow_append(gpb_handle* h, const double* X_new, const double* y_new, int64_t m, double* nlml,
+                        int32_t* info);
+int gpb_gpr_grow_predict(gpb_handle* h, const double* Z, int64_t mz, double* fz, double* cov);
+int64_t gpb_gpr_grow_size(gpb_handle* h);
+
 /* ---- dense factorisation on caller-owned device memory (np.linalg.cholesky, GPr.py:62) ---
  * In-place lower Cholesky of the n x n row-major matrix A_dev (leading dimension lda >= n,
  * n % 128 == 0, lda % 2 == 0); only the lower triangle is read and written. */

@@ -90,3 +90,34 @@ def test_rbf_kernel_matrix_and_ard(handle):
     gpm.optimize(max_iters=30)
     assert gpm.log_likelihood() > ll
     assert len(np.asarray(gpm.kern.lengthscale)) == 3
+
+
+def test_replay_loop_extends_the_factor(handle, monkeypatch):
+    """GP_parameter_fit.py:60-63: 40 prefixes, one more point each, a grid prediction after every set_XY.
+    The factor on the device must be EXTENDED (one rebuild at the start, none after) and every frame must
+    equal a refit from scratch."""
+    import gptest_b200.gpy_compat as GPy
+    from gptest_b200 import _lib
+    X, Y = script_data()
+    gpm = GPy.models.GPRegression(X, Y, GPy.kern.RBF(input_dim=2, variance=10., lengthscale=20.))
+    Xt, Yt = np.meshgrid(np.arange(0, 100, 7), np.arange(0, 100, 7))
+    Xgrid = np.vstack([Xt.ravel(), Yt.ravel()]).transpose().astype(float)
+    h = _lib.default_handle()
+    begins = []
+    real_begin = h.grow_begin
+    monkeypatch.setattr(h, 'grow_begin', lambda *a, **k: (begins.append(1), real_begin(*a, **k))[1])
+    for ii in range(40):
+        gpm.set_XY(X[0:ii + 1, :], Y[0:ii + 1] - MEAN_VALUE)
+        m, v = gpm.predict(Xgrid)
+        assert h.grow_size() == ii + 1
+        if ii in (0, 1, 17, 39):
+            rm, rv = gpr_oracle.predict_chol(log_hyp_of(gpm), X[:ii + 1], Y[:ii + 1, 0] - MEAN_VALUE, Xgrid)
+            assert np.abs(m[:, 0] - rm).max() <= 1e-8 * max(np.abs(rm).max(), 1e-3)
+            assert np.abs(v[:, 0] - (rv + gpm.likelihood.variance)).max() < 1e-8
+    assert len(begins) == 1
+    # changing a parameter invalidates the stored factor
+    gpm.kern.lengthscale = np.array([25.0])
+    m2, _ = gpm.predict(Xgrid)
+    assert len(begins) == 2
+    rm, _ = gpr_oracle.predict_chol(log_hyp_of(gpm), X[:40], Y[:40, 0] - MEAN_VALUE, Xgrid)
+    assert np.abs(m2[:, 0] - rm).max() <= 1e-8 * max(np.abs(rm).max(), 1e-3)
