@@ -399,6 +399,21 @@ def single_gpu_extras(h, X, y, Z, lh):
     tm = h.timings()
     out["fit_grad_ms"] = tm["total_ms"]                       # value + D+2 gradients: N^3 flop (potrf + trtri + U U^T)
     out["fit_grad_tflops"] = float(N_FIT) ** 3 / (tm["total_ms"] * 1e-3) / 1e12
+    # four independent hyper-parameter vectors in ONE call (multi-start / grid use): panels of all four share launches
+    kh4 = np.array([kh * (1.0 + 0.01 * i) for i in range(4)])
+    kh4[:, -1] = kh[-1]
+    h.gpr_nlml_batched(kh4)
+    t0 = time.perf_counter()
+    h.gpr_nlml_batched(kh4)
+    out["fits_per_s_batch_of_4"] = 4.0 / (time.perf_counter() - t0)
+    # appending 128 points to the stored factor of the first N-128 (gpb_gpr_grow_*) vs the refit above
+    h.grow_begin(kh, D_FIT, capacity=N_FIT)
+    h.grow_append(X[:N_FIT - 256], y[:N_FIT - 256])
+    h.grow_append(X[N_FIT - 256:N_FIT - 128], y[N_FIT - 256:N_FIT - 128])
+    t0 = time.perf_counter()
+    h.grow_append(X[N_FIT - 128:], y[N_FIT - 128:])
+    out["append_128_points_ms"] = (time.perf_counter() - t0) * 1e3
+    h.grow_begin(kh, D_FIT, capacity=1)                       # release the stored factor
     out["other_configs"] = other_configs(h)
     return out
 

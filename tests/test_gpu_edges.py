@@ -1,0 +1,122 @@
+"""Edge cases of the paths in SURVEY 8(a): tiny / ragged sizes, single test points, duplicated inputs, one pair,
+unreferenced items, one-class labels - each against the CPU oracle through the same C-ABI calls."""
+import numpy as np
+import pytest
+
+from oracle import gpr_oracle, gppref_oracle, gpc_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def natural(log_hyp):
+    from gptest_b200.sweep import natural_params
+    return natural_params(log_hyp)[0]
+
+
+@pytest.mark.parametrize('n,d', [(1, 1), (2, 3), (127, 2), (128, 2), (129, 2), (255, 9), (257, 17)])
+def test_gpr_ragged_sizes(handle, n, d):
+    rng = np.random.default_rng(n * 31 + d)
+    X = rng.random((n, d))
+    y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(n)
+    lh = np.log([0.7] * d + [1.3, 0.2])
+    handle.set_train(X, y)
+    v = handle.gpr_nlml(natural(lh))
+    ref = gpr_oracle.nlml_chol(lh, X, y)
+    assert abs(v - ref) <= 1e-8 * max(1.0, abs(ref))
+    for m in (1, 65):
+        Z = rng.random((m, d))
+        fz, cov = handle.gpr_predict(natural(lh), Z)
+        rf, rc = gpr_oracle.predict_chol(lh, X, y, Z)
+        assert fz.shape == (m,) and np.abs(fz - rf).max() <= 1e-9 * max(1.0, np.abs(rf).max())
+        assert np.abs(cov - rc).max() <= 1e-9
+    v2, g = handle.gpr_nlml(natural(lh), want_grad=True)
+    assert abs(v2 - ref) <= 1e-8 * max(1.0, abs(ref))
+    rg = gpr_oracle.nlml_grad(lh, X, y)
+    assert np.abs(g - rg).max() <= 1e-7 * max(1.0, np.abs(rg).max())
+
+
+def test_gpr_duplicated_inputs(handle):
+    """Repeated training points: fine with noise, LinAlgError without (np.linalg.cholesky, GPr.py:62)."""
+    rng = np.random.default_rng(0)
+    X = rng.random((50, 2))
+    X = np.vstack([X, X[:20]])
+    y = rng.standard_normal(70)
+    lh = np.log([0.5, 0.5, 1.0, 0.1])
+    handle.set_train(X, y)
+    ref = gpr_oracle.nlml_chol(lh, X, y)
+    assert abs(handle.gpr_nlml(natural(lh)) - ref) <= 1e-8 * abs(ref)
+    with pytest.raises(np.linalg.LinAlgError):
+        handle.gpr_nlml(natural(np.log([0.5, 0.5, 1.0, 1e-200])))
+    from gptest_b200 import GPr
+    gp = GPr.GaussianProcess(lh, 0, 0, "SE", "zero", "zero", X, y)
+    with pytest.raises(np.linalg.LinAlgError):
+        gp.compute_likelihood(np.log([0.5, 0.5, 1.0, 1e-200]))
+
+
+def test_gpr_constant_mean_argument(handle):
+    rng = np.random.default_rng(2)
+    X = rng.random((90, 2))
+    y = 5.0 + rng.standard_normal(90)
+    lh = np.log([0.5, 0.5, 1.0, 0.3])
+    handle.set_train(X, y)
+    v = handle.gpr_nlml(natural(lh), mean=5.0)
+    ref = gpr_oracle.nlml_chol(lh, X, y - 5.0)
+    assert abs(v - ref) <= 1e-9 * abs(ref)
+
+
+def pref_khyp(loghyp, d):
+    return np.concatenate([np.exp(loghyp[:d]), [np.exp(loghyp[d]) ** 2]])
+
+
+@pytest.mark.parametrize('n,pairs', [
+    (2, [(0, 1)]),                                   # one pair, two items
+    (9, [(0, 1)]),                                   # items that no pair mentions
+    (5, [(0, 1), (0, 1), (1, 0), (2, 3), (0, 1)]),   # repeated and reversed pairs
+    (130, [(i, (i * 7 + 1) % 130) for i in range(129)]),   # across a tile boundary
+])
+def test_pref_small_graphs(handle, n, pairs):
+    rng = np.random.default_rng(n)
+    x = rng.random((n, 2))
+    uvi = np.array(pairs, dtype=np.int64)
+    y = np.where(rng.random(len(pairs)) < 0.5, 1.0, -1.0).reshape(-1, 1)
+    lh = np.log([0.4, 0.6, 1.1, 0.1])
+    handle.set_train(x)
+    f, lml, iters, trace, jit = handle.pref_laplace(uvi, y, pref_khyp(lh, 2), sigma=1.0, delta_f=1e-7, max_iter=300)
+    of, olml, otrace = gppref_oracle.calc_laplace(x, uvi, y, lh, delta_f=1e-7, max_iter=300, return_trace=True)
+    assert iters == len(otrace)
+    assert np.abs(f.reshape(-1) - of.reshape(-1)).max() < 1e-6
+    assert abs(lml - olml) <= 1e-8 * max(1.0, abs(olml))
+
+
+@pytest.mark.parametrize('labels', ['all_plus', 'all_minus', 'single_minus'])
+def test_gpc_one_sided_labels(handle, labels):
+    rng = np.random.default_rng(4)
+    n = 140
+    x = rng.random((n, 2))
+    y = np.ones(n)
+    if labels == 'all_minus':
+        y = -y
+    if labels == 'single_minus':
+        y[17] = -1.0
+    lh = np.log([0.5, 0.5, 1.0])
+    handle.set_train(x)
+    kh = np.r_[np.exp(lh[:2]), np.exp(lh[2]) ** 2]
+    f, lml, iters, trace, jit = handle.gpc_laplace(y, kh, link=0, delta_f=1e-7)
+    of, olml = gpc_oracle.calc_laplace(x, y, lh, delta_f=1e-7)
+    assert np.abs(f - of).max() < 1e-6
+    assert abs(lml - olml) <= 1e-8 * max(1.0, abs(olml))
+    z = rng.random((1, 2))
+    mu, var, p = handle.gpc_predict(z)
+    omu, ovar, op = gpc_oracle.predict(x, y, lh, z, delta_f=1e-7)
+    assert abs(p[0] - op[0]) < 1e-7
+
+
+def test_argument_errors(handle):
+    from gptest_b200._lib import GpbError
+    X = np.random.default_rng(0).random((10, 2))
+    handle.set_train(X)                                  # no targets
+    with pytest.raises(GpbError, match='targets'):
+        handle.gpr_nlml(np.array([1.0, 1.0, 1.0, 0.1]))
+    with pytest.raises(GpbError):
+        handle.pref_laplace(np.array([[0, 10]], dtype=np.int64), np.ones((1, 1)), np.array([1.0, 1.0, 1.0]),
+                            sigma=1.0, delta_f=1e-6, max_iter=10)      # item index out of range
