@@ -133,3 +133,17 @@ class PreferenceGaussianProcess(object):
         """GPpref.py:159-161."""
         f, lml = self.calc_laplace(loghyp)
         return -lml
+
+    # ---- opt-in extensions, NOT in the reference (SURVEY 8f rank 3; include/gpb200.h gpb_pref_evidence/_predict) ----
+    # They use the state calc_laplace left on the device: call them right after it.
+    def laplace_evidence(self):
+        """R&W eq. 3.32 at the mode: sum log Phi(z) - f'K^-1 f/2 - log|I + K W|/2 (what GPpref.py:90-94 leaves out)."""
+        return _handle().pref_evidence()
+
+    def predict_latent(self, x_test):
+        """Posterior mean and variance of the latent utility at new items: ((m,), (m,))."""
+        return _handle().pref_predict(x_test)
+
+    def predict_preference(self, x_a, x_b):
+        """Posterior of f(x_b) - f(x_a) and P(x_b preferred to x_a) = Phi(mean / sqrt(2 sigma^2 + var))."""
+        return _handle().pref_predict(x_a, x_b)

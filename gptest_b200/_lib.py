@@ -55,6 +55,8 @@ SIGNATURES = {
     'gpb_gpc_predict': (C.c_int, [C.c_void_p, c_dp, C.c_int64, c_dp, c_dp, c_dp]),
     'gpb_pref_laplace': (C.c_int, [C.c_void_p, c_lp, c_dp, C.c_int64, c_dp, C.c_double, C.c_double, C.c_int32,
                                    C.c_int32, C.c_int32, c_dp, c_dp, c_ip, c_dp, c_dp, c_ip]),
+    'gpb_pref_evidence': (C.c_int, [C.c_void_p, c_dp]),
+    'gpb_pref_predict': (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int64, c_dp, c_dp, c_dp]),
     'gpb_pref_derivatives': (C.c_int, [C.c_void_p, c_lp, c_dp, C.c_int64, C.c_int64, c_dp, C.c_double,
                                        C.c_int32, c_dp, c_dp]),
     'gpb_microbench': (C.c_int, [C.c_void_p, C.c_int32, c_dp]),
@@ -359,6 +361,30 @@ def _gpc_predict(self, Z):
     return mu, var, p
 
 
+def _pref_evidence(self):
+    """R&W eq. 3.32 at the mode of the last pref_laplace (opt-in, not in the reference)."""
+    v = np.empty(1)
+    self.check(self.lib.gpb_pref_evidence(self.h, _dp(v)))
+    return float(v[0])
+
+
+def _pref_predict(self, Z, Zb=None):
+    """Latent posterior at Z, or of f(Zb) - f(Z) plus the preference probability (opt-in, not in the reference)."""
+    Z = as_f64(Z)
+    Z = Z.reshape(len(Z), -1)
+    m = len(Z)
+    mean, var = np.empty(m), np.empty(m)
+    if Zb is None:
+        self.check(self.lib.gpb_pref_predict(self.h, _dp(Z), None, m, _dp(mean), _dp(var), None))
+        return mean, var
+    Zb = as_f64(Zb).reshape(m, -1)
+    prob = np.empty(m)
+    self.check(self.lib.gpb_pref_predict(self.h, _dp(Z), _dp(Zb), m, _dp(mean), _dp(var), _dp(prob)))
+    return mean, var, prob
+
+
+Handle.pref_evidence = _pref_evidence
+Handle.pref_predict = _pref_predict
 Handle.pref_laplace = _pref_laplace
 Handle.pref_derivatives = _pref_derivatives
 Handle.gpc_laplace = _gpc_laplace

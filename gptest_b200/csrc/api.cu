@@ -34,7 +34,8 @@ double* gpb_handle::pinned(size_t bytes) {
 #define GPB_API_BEGIN                                       \
   if (!h) return -1;                                        \
   try {                                                     \
-    GPB_CUDA(cudaSetDevice(h->device));
+    GPB_CUDA(cudaSetDevice(h->device));                     \
+    ++h->ws_epoch;
 #define GPB_API_END                                         \
   }                                                         \
   catch (const gpb::Error& e) {                             \
@@ -211,6 +212,7 @@ int gpb_destroy(gpb_handle* h) {
   for (auto e : h->tev) if (e) cudaEventDestroy(e);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   gpb::grow_release(h);
+  if (h->pref_state && h->pref_state_free) h->pref_state_free(h->pref_state);
   delete h;
   return 0;
 }

@@ -19,6 +19,7 @@ extern "C" int gpb_gpr_nlml_batched(gpb_handle* h, const double* khyp, int64_t B
                                     double* grad, int32_t* info) {
   if (!h) return -1;
   try {
+    ++h->ws_epoch;
     GPB_CUDA(cudaSetDevice(h->device));
     GPB_REQUIRE(h->n > 0 && h->has_y, "no training data: call gpb_set_train first");
     GPB_REQUIRE(khyp && nlml && B > 0, "null argument");

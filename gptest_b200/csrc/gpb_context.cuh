@@ -89,6 +89,12 @@ struct gpb_handle {
   int lap_link = 0;
   std::vector<double> lap_khyp;
 
+  // The Laplace entry points leave their factor / mode in the shared work space for the predict calls; any other
+  // call that uses the work space bumps ws_epoch, which invalidates that state (checked, never silent).
+  uint64_t ws_epoch = 0, state_epoch = ~0ull;
+  void* pref_state = nullptr;                 // laplace.cu: what gpb_pref_evidence / gpb_pref_predict need
+  void (*pref_state_free)(void*) = nullptr;
+
   gpb::GrowState* grow = nullptr;     // gpb_gpr_grow_* state (own buffers: other calls do not disturb it)
 
   cudaEvent_t next_event();

@@ -178,7 +178,7 @@ void trsv_lt(gpb_handle* h, const FactorMat& m, double* r, double* x) {
 // FactorMat over h->A with the (2 np + 128)-row layout shared with grad.cu
 FactorMat laplace_mat(gpb_handle* h, int64_t rows_total) {
   const int64_t np = h->n_pad;
-  const int64_t rows_alloc = 2 * np + TILE;
+  const int64_t rows_alloc = 3 * np + TILE;     // factor | appended tile row | scratch S1 (np rows) | scratch S2 (np rows)
   FactorMat m;
   m.ld = np; m.n_pad = np; m.rows_total = rows_total; m.batch = 1;
   m.batch_stride = rows_alloc * np;
@@ -505,12 +505,110 @@ __global__ void __launch_bounds__(256) gpc_predict_finish_kernel(const double* _
   }
 }
 
+// ---- state kept by gpb_pref_laplace for gpb_pref_evidence / gpb_pref_predict ------------------------------
+struct PrefState {
+  int64_t n = 0, P = 0;
+  double sigma = 1.0, eps = 0.0, lml_ref = 0.0, half_logdet_k = 0.0;
+  int grad_mode = 0;
+  bool factored = false;          // chol(K^-1 + W(f_hat)) is in the work space
+  double sum_log_g = 0.0;         // sum log diag of that factor
+  std::vector<double> khyp;
+  PrefDev pd;
+};
+void pref_state_free(void* p) { delete static_cast<PrefState*>(p); }
+
+// rows <- rows_b - rows (difference of two covariance row blocks); one CTA per row
+__global__ void rows_sub_kernel(double* __restrict__ rows, const double* __restrict__ rows_b, int64_t ld, int64_t ncols) {
+  double* r = rows + blockIdx.x * ld;
+  const double* q = rows_b + blockIdx.x * ld;
+  for (int64_t j = threadIdx.x; j < ncols; j += blockDim.x) r[j] = q[j] - r[j];
+}
+// k** of the quantity predicted: sf2 for one item, k(a,a) + k(b,b) - 2 k(a,b) for a difference (scaled points, pitch ld_t)
+__global__ void pref_kss_kernel(const double* __restrict__ zaT, const double* __restrict__ zbT, int64_t ld_t, int d, int64_t m,
+                                double sf2, double* __restrict__ kss) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= m) return;
+  if (!zbT) { kss[i] = sf2; return; }
+  double r2 = 0.0;
+  for (int k = 0; k < d; ++k) {
+    const double t = zaT[k * ld_t + i] - zbT[k * ld_t + i];
+    r2 = fma(t, t, r2);
+  }
+  kss[i] = 2.0 * sf2 - 2.0 * sf2 * exp(-0.5 * r2);
+}
+// q1_i = R_i . T_i (two row blocks with the same pitch)
+__global__ void __launch_bounds__(256) rows_dot2_kernel(const double* __restrict__ R, const double* __restrict__ T, int64_t ld,
+                                                        int64_t ncols, double* __restrict__ out) {
+  __shared__ double sh[256];
+  const double* r = R + blockIdx.x * ld;
+  const double* t = T + blockIdx.x * ld;
+  double s = 0.0;
+  for (int64_t j = threadIdx.x; j < ncols; j += 256) s = fma(r[j], t[j], s);
+  const double ss = cta_sum<256>(s, sh);
+  if (threadIdx.x == 0) out[blockIdx.x] = ss;
+}
+// var_i = kss_i - q1_i + |V_i|^2 ; prob_i = Phi(mean_i / sqrt(2 sigma^2 + var_i)) for differences
+__global__ void __launch_bounds__(256) pref_predict_finish_kernel(const double* __restrict__ V, int64_t ld, int64_t ncols,
+                                                                  const double* __restrict__ kss, const double* __restrict__ q1,
+                                                                  const double* __restrict__ mean, double two_sigma2,
+                                                                  double* __restrict__ var, double* __restrict__ prob) {
+  __shared__ double sh[256];
+  const double* r = V + blockIdx.x * ld;
+  double s = 0.0;
+  for (int64_t j = threadIdx.x; j < ncols; j += 256) s = fma(r[j], r[j], s);
+  const double ss = cta_sum<256>(s, sh);
+  if (threadIdx.x == 0) {
+    const double v = kss[blockIdx.x] - q1[blockIdx.x] + ss;
+    var[blockIdx.x] = v;
+    if (prob) prob[blockIdx.x] = normcdf(mean[blockIdx.x] / sqrt(two_sigma2 + fmax(v, 0.0)));
+  }
+}
+
+// chol(K^-1 + W(f_hat)) into the work space (the loop leaves the factor of the PREVIOUS iterate there)
+void pref_factor_at_mode(gpb_handle* h, PrefState* ps) {
+  if (ps->factored) return;
+  const int64_t n = ps->n, np = h->n_pad;
+  FactorMat g = laplace_mat(h, np);
+  const double* iK = h->aux2.as<double>();
+  double* f = h->aux0.as<double>();
+  const double isq = 1.0 / (ps->sigma * std::sqrt(2.0)), i2v = isq * isq;
+  pref_pair_kernel<<<static_cast<unsigned>((ps->P + 255) / 256), 256, 0, h->s0>>>(ps->pd.uvi, ps->pd.y, ps->P, f, isq, i2v,
+                                                                               ps->pd.dk, ps->pd.wk);
+  scale_copy_lower_kernel<<<static_cast<unsigned>(np), 256, 0, h->s0>>>(iK, np, g.A, g.ld, nullptr, 0.0);
+  pref_row_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, h->s0>>>(n, ps->pd.gr, ps->pd.dk, ps->pd.wk, f, 1, g.A,
+                                                                            g.ld, nullptr, nullptr, nullptr);
+  GPB_CUDA(cudaGetLastError());
+  GPB_CUDA(cudaMemsetAsync(g.info, 0, 4, h->s0));
+  chol_sweep(h, g, true);
+  double* sc = h->scal.as<double>();
+  sum_log_kernel<<<1, 512, 0, h->s0>>>(g.diag, np, sc + 8);
+  GPB_CUDA(cudaGetLastError());
+  h->launches += 4;
+  double* host = h->pinned(64);
+  GPB_CUDA(cudaMemcpyAsync(host, sc + 8, 8, cudaMemcpyDeviceToHost, h->s0));
+  GPB_CUDA(cudaMemcpyAsync(host + 1, g.info, 4, cudaMemcpyDeviceToHost, h->s0));
+  GPB_CUDA(cudaStreamSynchronize(h->s0));
+  if (*reinterpret_cast<int*>(host + 1)) throw Error{"K^-1 + W is not positive definite at the mode"};
+  ps->sum_log_g = host[0];
+  ps->factored = true;
+}
+
+PrefState* pref_state_checked(gpb_handle* h) {
+  PrefState* ps = static_cast<PrefState*>(h->pref_state);
+  // the entry macro has already counted this call: the state is current iff nothing else ran in between
+  GPB_REQUIRE(ps != nullptr && ps->n == h->n && h->state_epoch + 1 == h->ws_epoch,
+              "no preference Laplace state on this handle: call gpb_pref_laplace first (any other call that uses "
+              "the work space invalidates it)");
+  return ps;
+}
+
 }  // namespace
 
 #define LAP_BEGIN                                      \
   if (!h) return -1;                                   \
   try {                                                \
-    GPB_CUDA(cudaSetDevice(h->device));
+    GPB_CUDA(cudaSetDevice(h->device));                \
+    ++h->ws_epoch;
 #define LAP_END                                        \
   }                                                    \
   catch (const gpb::Error& e) {                        \
@@ -641,6 +739,16 @@ int gpb_pref_laplace(gpb_handle* h, const int64_t* uvi, const double* y, int64_t
   GPB_CUDA(cudaEventElapsedTime(&h->timings[1], h->tev[1], h->tev[2]));
   GPB_CUDA(cudaEventElapsedTime(&h->timings[4], h->tev[0], h->tev[2]));
   h->lap_n = 0;
+  {
+    GPB_CUDA(cudaMemcpy(host, sc, 8, cudaMemcpyDeviceToHost));
+    if (h->pref_state) pref_state_free(h->pref_state);
+    PrefState* ps = new PrefState;
+    h->pref_state = ps;
+    h->pref_state_free = pref_state_free;
+    ps->n = n; ps->P = P; ps->sigma = sigma; ps->eps = eps; ps->lml_ref = last_lml; ps->half_logdet_k = host[0];
+    ps->grad_mode = grad_mode; ps->khyp.assign(khyp, khyp + h->d + 1); ps->pd = pd;
+    h->state_epoch = h->ws_epoch;
+  }
   LAP_END
 }
 
@@ -731,6 +839,7 @@ int gpb_gpc_laplace(gpb_handle* h, const double* y, const double* khyp, int32_t 
   GPB_CUDA(cudaEventElapsedTime(&h->timings[4], h->tev[0], h->tev[1]));
   // state for gpb_gpc_predict: L and Dinv (in h->A / h->Dinv), sW, grad, kernel parameters
   h->lap_n = n;
+  h->state_epoch = h->ws_epoch;
   h->lap_link = link;
   h->lap_khyp.assign(khyp, khyp + h->d + 1);
   LAP_END
@@ -738,7 +847,9 @@ int gpb_gpc_laplace(gpb_handle* h, const double* y, const double* khyp, int32_t 
 
 int gpb_gpc_predict(gpb_handle* h, const double* Z, int64_t mz, double* mu, double* var, double* prob) {
   LAP_BEGIN
-  GPB_REQUIRE(h->lap_n == h->n && h->n > 0, "no Laplace state on this handle: call gpb_gpc_laplace first");
+  GPB_REQUIRE(h->lap_n == h->n && h->n > 0 && h->state_epoch + 1 == h->ws_epoch,
+              "no Laplace state on this handle: call gpb_gpc_laplace first (any other call that uses the work space "
+              "invalidates it)");
   GPB_REQUIRE(Z && mu && var && prob && mz > 0, "null argument");
   const int64_t np = h->n_pad;
   const int nt = static_cast<int>(np / TILE);
@@ -784,6 +895,102 @@ int gpb_gpc_predict(gpb_handle* h, const double* Z, int64_t mz, double* mu, doub
     GPB_CUDA(cudaMemcpyAsync(prob + z0, o + 2 * cap, mc * 8, cudaMemcpyDeviceToHost, h->s0));
     GPB_CUDA(cudaStreamSynchronize(h->s0));
   }
+  h->state_epoch = h->ws_epoch;                // the state is still current: predict again without refitting
+  LAP_END
+}
+
+int gpb_pref_evidence(gpb_handle* h, double* evidence) {
+  LAP_BEGIN
+  GPB_REQUIRE(evidence, "null argument");
+  PrefState* ps = pref_state_checked(h);
+  pref_factor_at_mode(h, ps);
+  // lml_ref = sum log Phi - f'K^-1 f/2 - (1/2) sum log diag L_K - n/2 log 2pi   (GPpref.py:90-94,131)
+  // evidence = sum log Phi - f'K^-1 f/2 - sum log diag L_K - sum log diag chol(K^-1 + W)        (R&W eq. 3.32)
+  *evidence = ps->lml_ref - 0.5 * ps->half_logdet_k + 0.5 * static_cast<double>(ps->n) * 1.8378770664093453 - ps->sum_log_g;
+  h->state_epoch = h->ws_epoch;
+  LAP_END
+}
+
+int gpb_pref_predict(gpb_handle* h, const double* Z, const double* Zb, int64_t mz, double* mean, double* var, double* prob) {
+  LAP_BEGIN
+  GPB_REQUIRE(Z && mean && var && mz > 0 && (prob || !Zb), "null argument");
+  PrefState* ps = pref_state_checked(h);
+  pref_factor_at_mode(h, ps);
+  const int64_t np = h->n_pad;
+  const int d = h->d;
+  FactorMat m = laplace_mat(h, np);
+  const double* iK = h->aux2.as<double>();
+  double* f = h->aux0.as<double>();
+  double* alpha = f + 2 * np;                                     // K^-1 f_hat
+  launch_row_dot(iK, np, 0, f, 0, np, np, 0, alpha, 0, 1, h->s0);
+  ++h->launches;
+  const double *ell, *hyp2;
+  upload_kernel_params(h, ps->khyp.data(), ps->eps, &ell, &hyp2);
+  const double sf2 = ps->khyp[d];
+  double* S1 = m.A + (np + TILE) * m.ld;                          // R = k* rows (np rows available)
+  double* S2 = m.A + (2 * np + TILE) * m.ld;                      // T = R K^-1, then V = T L_G^-T
+  TileMaps map_ik;
+  make_tile_maps(&map_ik, iK, np, np, 1, np, np * np);
+  const int64_t cap = np;
+  h->outv.ensure(static_cast<size_t>(cap) * 8 * 5);
+  double* o = h->outv.as<double>();                               // mean | var | prob | kss | q1
+  h->Zd.ensure(static_cast<size_t>(cap) * d * 8 * 2);
+  h->ZsT.ensure(static_cast<size_t>(d) * cap * 8 * 2);
+  h->zsq.ensure(static_cast<size_t>(cap) * 8 * 2);
+  for (int64_t z0 = 0; z0 < mz; z0 += cap) {
+    const int64_t mc = mz - z0 < cap ? mz - z0 : cap;
+    const int64_t mp64 = round_up(mc, 64);
+    double* zd = h->Zd.as<double>();
+    double* zsT = h->ZsT.as<double>();
+    double* zsq = h->zsq.as<double>();
+    auto cov_rows = [&](const double* Zsrc, int slot, double* dst) {
+      GPB_CUDA(cudaMemcpyAsync(zd + slot * cap * d, Zsrc + z0 * d, static_cast<size_t>(mc) * d * 8, cudaMemcpyHostToDevice, h->s0));
+      launch_se_prep(zd + slot * cap * d, mc, d, ell, zsT + slot * d * cap, mp64, zsq + slot * cap, 1, 0, 0, 0, h->s0);
+      SeArgs a{};
+      a.rT = zsT + slot * d * cap; a.r_ld = mp64; a.r_sq = zsq + slot * cap; a.n_rows_valid = mc;
+      a.cT = h->XsT.as<double>(); a.c_ld = np; a.c_sq = h->sq.as<double>(); a.n_cols_valid = h->n;
+      a.d = d; a.out = dst; a.ld = m.ld; a.rows_pad = mp64; a.cols_pad = np;
+      a.hyp_dev = hyp2; a.mode = 2; a.clip = 1;                   // GPy RBF semantics, as in the fit (GPpref.py:122)
+      launch_se_build(a, 1, h->s0);
+      h->launches += 2;
+    };
+    cov_rows(Z, 0, S1);
+    if (Zb) {
+      cov_rows(Zb, 1, S2);
+      rows_sub_kernel<<<static_cast<unsigned>(mc), 256, 0, h->s0>>>(S1, S2, m.ld, np);      // rows of f(b) - f(a)
+      ++h->launches;
+    }
+    pref_kss_kernel<<<static_cast<unsigned>((mc + 255) / 256), 256, 0, h->s0>>>(zsT, Zb ? zsT + d * cap : nullptr, mp64, d, mc,
+                                                                                sf2, o + 3 * cap);
+    launch_row_dot(S1, m.ld, 0, alpha, 0, mc, np, 0, o, 0, 1, h->s0);                        // mean = R K^-1 f
+    {
+      GemmArgs a{};                                               // T = R * iK^T (iK symmetric), 64-tiles
+      a.C = S2; a.ldc = m.ld; a.c_batch_stride = 0; a.rows_total = static_cast<int>(mp64);
+      a.j0 = 0; a.j1 = static_cast<int>(np / 64); a.R = static_cast<int>(mp64 / 64); a.tri = 0; a.i0 = 0;
+      a.ka0 = 0; a.kb0 = 0; a.nk = static_cast<int>(np / GEMM_KB);
+      a.a_row0 = static_cast<int>(np + TILE); a.b_row0 = 0; a.epi = 0;
+      launch_dmma_gemm(m.mapA.m64, map_ik.m64, a, 1, h->s0, 64);
+    }
+    rows_dot2_kernel<<<static_cast<unsigned>(mc), 256, 0, h->s0>>>(S1, S2, m.ld, np, o + 4 * cap);   // q1 = R K^-1 R'
+    GPB_CUDA(cudaGetLastError());
+    h->launches += 4;
+    m.rows_total = 2 * np + TILE + mc;
+    SweepPlan plan;
+    plan.factor = false;
+    plan.extra_tile0 = static_cast<int>((2 * np + TILE) / TILE);
+    plan.extra_tiles = static_cast<int>((mc + TILE - 1) / TILE);
+    chol_sweep(h, m, plan);                                       // V = T L_G^-T
+    pref_predict_finish_kernel<<<static_cast<unsigned>(mc), 256, 0, h->s0>>>(S2, m.ld, np, o + 3 * cap, o + 4 * cap, o,
+                                                                            2.0 * ps->sigma * ps->sigma, o + cap,
+                                                                            Zb ? o + 2 * cap : nullptr);
+    GPB_CUDA(cudaGetLastError());
+    ++h->launches;
+    GPB_CUDA(cudaMemcpyAsync(mean + z0, o, mc * 8, cudaMemcpyDeviceToHost, h->s0));
+    GPB_CUDA(cudaMemcpyAsync(var + z0, o + cap, mc * 8, cudaMemcpyDeviceToHost, h->s0));
+    if (Zb) GPB_CUDA(cudaMemcpyAsync(prob + z0, o + 2 * cap, mc * 8, cudaMemcpyDeviceToHost, h->s0));
+    GPB_CUDA(cudaStreamSynchronize(h->s0));
+  }
+  h->state_epoch = h->ws_epoch;
   LAP_END
 }
 

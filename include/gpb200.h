@@ -144,6 +144,19 @@ int gpb_pref_laplace(gpb_handle* h, const int64_t* uvi, const double* y, int64_t
                      const double* khyp, double sigma, double delta_f, int32_t max_iter,
                      int32_t grad_mode, int32_t use_f0, double* f_inout, double* lml,
                      int32_t* iters, double* trace, double* jitter, int32_t* info);
+/* Opt-in extensions beyond the reference.  Both use the state the LAST gpb_pref_laplace left on
+ * the handle (mode, K^-1, comparison graph); any other call that uses the work space invalidates it (error, not
+ * garbage).  W is re-evaluated at the returned mode and K^-1 + W factored once, on first use.
+ * gpb_pref_evidence: the Laplace approximation of the log evidence, R&W eq. 3.32:
+ *   sum_k log Phi(z_k) - f' K^-1 f / 2 - log|I + K W| / 2
+ *   (the reference's log_marginal, GPpref.py:90-94, has no W term and counts log|K| a quarter, GPpref.py:131).
+ * gpb_pref_predict: latent posterior at mz test items Z (host, mz x d): mean = k*' K^-1 f and
+ *   var = k** - k*' (K + W^-1)^-1 k* = k** - k*' K^-1 k* + (K^-1 k*)' (K^-1 + W)^-1 (K^-1 k*)   (W singular: never inverted).
+ *   With Zb != NULL the same for the difference f(Zb_i) - f(Z_i), and prob_i = Phi(mean_i / sqrt(2 sigma^2 + var_i)):
+ *   the probability that Zb_i is preferred to Z_i (the likelihood of GPpref.py:56-66 under the posterior). */
+int gpb_pref_evidence(gpb_handle* h, double* evidence);
+int gpb_pref_predict(gpb_handle* h, const double* Z, const double* Zb, int64_t mz, double* mean, double* var,
+                     double* prob);
 /* PrefProbit.derivatives (GPpref.py:68-88) on its own: dense W (n x n) and gradient (n). */
 int gpb_pref_derivatives(gpb_handle* h, const int64_t* uvi, const double* y, int64_t P, int64_t n,
                          const double* f, double sigma, int32_t grad_mode, double* W_out, double* g_out);

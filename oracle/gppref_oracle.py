@@ -157,3 +157,57 @@ def calc_laplace(x, uvi, y, loghyp, delta_f=1e-6, f=None, max_iter=None, return_
     if return_trace:
         return f, lml, trace
     return f, lml
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Opt-in extensions.  NOT in the reference: its log_marginal (GPpref.py:90-94) has no W term
+# and it has no prediction at all.  Restated from Rasmussen & Williams ch. 3 for the checker of
+# gpb_pref_evidence / gpb_pref_predict; parity is unpinned by construction.
+# ---------------------------------------------------------------------------------------------------------
+def _k_and_w(x, uvi, y, loghyp, f, sigma, eps):
+    x = np.asarray(x, dtype=float).reshape(len(x), -1)
+    d = x.shape[1]
+    ell = np.exp(loghyp[:d])
+    sf2 = np.exp(loghyp[d]) ** 2
+    K = rbf_ard_K(x, ell, sf2) + eps * np.eye(len(x))          # the jittered matrix the fit used (GPpref.py:123-128)
+    lik = ProbitPrefOracle(sigma)
+    f = np.asarray(f, dtype=float).reshape(-1, 1)
+    W, _ = lik.derivatives(np.asarray(uvi), np.asarray(y, dtype=float).reshape(-1, 1), f, accumulate=True)
+    return x, ell, sf2, K, W, lik, f
+
+
+def laplace_evidence(x, uvi, y, loghyp, f, sigma=1.0, eps=1e-6):
+    """R&W eq. 3.32 at the mode f: sum log Phi(z) - f' K^-1 f / 2 - log|I + K W| / 2."""
+    x, ell, sf2, K, W, lik, f = _k_and_w(x, uvi, y, loghyp, f, sigma, eps)
+    z = lik.z_k(np.asarray(uvi), f, np.asarray(y, dtype=float).reshape(-1, 1))
+    iK = np.linalg.inv(K)
+    sign, logdet = np.linalg.slogdet(np.eye(len(x)) + K @ W)
+    return float(np.sum(np.log(ndtr(z))) - 0.5 * (f.T @ iK @ f).flat[0] - 0.5 * logdet)
+
+
+def predict_latent(x, uvi, y, loghyp, f, z, zb=None, sigma=1.0, eps=1e-6):
+    """Latent posterior at test items z (or of the difference f(zb) - f(z)): mean k*' K^-1 f,
+    var k** - k*' (K + W^-1)^-1 k* written without W^-1 (W is singular):
+    k** - k*' K^-1 k* + (K^-1 k*)' (K^-1 + W)^-1 (K^-1 k*).  With zb also Phi(mean / sqrt(2 sigma^2 + var))."""
+    x, ell, sf2, K, W, lik, f = _k_and_w(x, uvi, y, loghyp, f, sigma, eps)
+
+    def cross(zz):
+        zz = np.asarray(zz, dtype=float).reshape(len(zz), -1)
+        xs, zs = x / ell, zz / ell
+        r2 = np.clip(np.sum(zs * zs, 1)[:, None] + np.sum(xs * xs, 1)[None, :] - 2 * zs @ xs.T, 0, np.inf)
+        return sf2 * np.exp(-0.5 * r2), zs                       # (m, n)
+
+    R, zs = cross(z)
+    kss = np.full(len(R), sf2)
+    if zb is not None:
+        Rb, zbs = cross(zb)
+        R = Rb - R
+        kss = 2 * sf2 - 2 * sf2 * np.exp(-0.5 * np.sum((zs - zbs) ** 2, axis=1))
+    iK = np.linalg.inv(K)
+    T = R @ iK
+    mean = (T @ f)[:, 0]
+    G = iK + W
+    var = kss - np.sum(R * T, axis=1) + np.sum(T * np.linalg.solve(G, T.T).T, axis=1)
+    if zb is None:
+        return mean, var
+    return mean, var, ndtr(mean / np.sqrt(2 * sigma ** 2 + np.maximum(var, 0)))

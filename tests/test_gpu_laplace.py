@@ -157,3 +157,66 @@ def test_gpc_dropin_module(handle):
         GPc.ClassifierGaussianProcess(x, np.full(260, 2))
     assert GPc.ClassifierLikelihood('Logit').link_id == 1 and GPc.ClassifierLikelihood().link_id == 0
     assert abs(GPc.logistic_function(0.0) - 0.5) < 1e-16
+
+
+# ---- opt-in extensions: evidence and prediction, against the dense numpy restatement -----
+@pytest.mark.parametrize("n,P,D,newton", [(60, 200, 2, True), (300, 1500, 3, True), (200, 700, 2, False)])
+def test_pref_evidence_and_prediction(handle, n, P, D, newton):
+    x, uvi, y = make_pref(n, P, D, seed=n + P)
+    lh = np.log([0.4] * D + [1.2, 0.1])
+    handle.set_train(x)
+    f, lml, iters, trace, jit = handle.pref_laplace(uvi, y, pref_khyp(lh, D), sigma=1.0, delta_f=1e-9, max_iter=400,
+                                                    grad_mode=1 if newton else 0)
+    ev = handle.pref_evidence()
+    ref = gppref_oracle.laplace_evidence(x, uvi, y, lh, f, sigma=1.0, eps=jit)
+    assert abs(ev - ref) <= 1e-8 * max(1.0, abs(ref))
+    rng = np.random.default_rng(7)
+    za, zb = rng.random((130, D)), rng.random((130, D))
+    mu, var = handle.pref_predict(za)
+    rmu, rvar = gppref_oracle.predict_latent(x, uvi, y, lh, f, za, eps=jit)
+    # k** - k*'K^-1 k* cancels to ~1e-6 * sf2 with the 1e-6 jitter: absolute tolerance on the prior scale
+    assert np.abs(mu - rmu).max() <= 1e-7 * max(1.0, np.abs(rmu).max())
+    assert np.abs(var - rvar).max() <= 1e-7
+    dmu, dvar, p = handle.pref_predict(za, zb)
+    rdmu, rdvar, rp = gppref_oracle.predict_latent(x, uvi, y, lh, f, za, zb, eps=jit)
+    assert np.abs(dmu - rdmu).max() <= 1e-7 * max(1.0, np.abs(rdmu).max())
+    assert np.abs(dvar - rdvar).max() <= 1e-7
+    assert np.abs(p - rp).max() <= 1e-7 and ((p > 0) & (p < 1)).all()
+    # symmetry: swapping the items flips the mean and the probability
+    dmu2, dvar2, p2 = handle.pref_predict(zb, za)
+    assert np.abs(dmu + dmu2).max() < 1e-9 and np.abs(p + p2 - 1).max() < 1e-9
+    # training items predict their own mode
+    mu_t, var_t = handle.pref_predict(x[:50])
+    assert np.abs(mu_t - f[:50]).max() < 1e-5
+
+
+def test_pref_state_is_invalidated_by_other_calls(handle):
+    from gptest_b200._lib import GpbError
+    x, uvi, y = make_pref(50, 120, 2, seed=1)
+    lh = np.log([0.4, 0.4, 1.2, 0.1])
+    handle.set_train(x)
+    handle.pref_laplace(uvi, y, pref_khyp(lh, 2), sigma=1.0, delta_f=1e-6, max_iter=100)
+    handle.pref_evidence()
+    handle.pref_predict(x[:3])                     # the state survives its own readers
+    handle.kxx(np.array([0.4, 0.4, 1.0, 0.0]))     # ... but not a call that uses the work space
+    with pytest.raises(GpbError, match='gpb_pref_laplace first'):
+        handle.pref_evidence()
+    yc = np.where(np.arange(50) % 2 == 0, 1.0, -1.0)
+    handle.gpc_laplace(yc, np.array([0.4, 0.4, 1.0]))
+    handle.gpc_predict(x[:3])
+    handle.gpc_predict(x[:3])
+    handle.kxx(np.array([0.4, 0.4, 1.0, 0.0]))
+    with pytest.raises(GpbError, match='gpb_gpc_laplace first'):
+        handle.gpc_predict(x[:3])
+
+
+def test_gppref_dropin_extensions(handle):
+    from gptest_b200 import GPpref
+    x, uvi, y, lh = PREF['k3_x'], PREF['k3_uvi'], PREF['k3_y'], PREF['k3_loghyp']
+    gp = GPpref.PreferenceGaussianProcess(x, uvi, y, delta_f=1e-9, newton=True)
+    f, lml = gp.calc_laplace(lh)
+    ev = gp.laplace_evidence()
+    ref = gppref_oracle.laplace_evidence(x, uvi, y, lh, f, eps=gp.jitter)
+    assert abs(ev - ref) <= 1e-8 * max(1.0, abs(ref))
+    mu, var, p = gp.predict_preference(x[:5], x[5:10])
+    assert p.shape == (5,) and np.all(var > -1e-9)
