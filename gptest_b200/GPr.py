@@ -45,8 +45,8 @@ class GaussianProcess(object):
         self.trainInput = trainInput
         self.trainTarget = trainTarget
         # GPr.py:28-42: string dispatch, unknown names give []
-        if covFunName == "SE":
-            self.covFun = SquaredExponential(log_hyp, trainInput)
+        if covFunName in COVARIANCE_FUNCTIONS:        # "SE" in the reference; the Matern names are extensions
+            self.covFun = COVARIANCE_FUNCTIONS[covFunName](log_hyp, trainInput)
         else:
             self.covFun = []
         if meanFunName == "zero":
@@ -67,28 +67,32 @@ class GaussianProcess(object):
         cov = self.covFun
         h = _handle()
         h.set_train(cov.x, self.trainTarget)           # GPr.py:52 uses trainTarget as is (no mean)
-        fz, cov_fz = h.gpr_predict(cov.khyp(), testInput)
+        fz, cov_fz = h.gpr_predict(cov.khyp(), testInput, kind=cov.KIND)
         return fz, cov_fz
 
     def compute_likelihood(self, hyp):
         """GPr.py:57-69: negative log marginal likelihood for ``hyp``; returns a (1,1) array."""
-        covSE = SquaredExponential(hyp, self.trainInput)          # GPr.py:59 (kernel from the argument)
+        covSE = self._cov_class()(hyp, self.trainInput)           # GPr.py:59 (kernel from the argument)
         m = self.meanFun.y                                        # GPr.py:61
         y = np.reshape(self.trainTarget, (len(self.trainTarget), 1))   # GPr.py:64
         h = _handle()
         h.set_train(covSE.x, (y - m).reshape(-1))
-        nlml = h.gpr_nlml(covSE.khyp())
+        nlml = h.gpr_nlml(covSE.khyp(), kind=covSE.KIND)
         return np.array([[nlml]])
 
     def compute_likelihood_and_gradient(self, hyp):
         """Value and gradient w.r.t. the log hyper-parameters (not in the reference, which uses
         Nelder-Mead; this is what GPy's L-BFGS in GP_parameter_fit.py:32-33 consumes)."""
-        covSE = SquaredExponential(hyp, self.trainInput)
+        covSE = self._cov_class()(hyp, self.trainInput)
         m = self.meanFun.y
         y = np.reshape(self.trainTarget, (len(self.trainTarget), 1))
         h = _handle()
         h.set_train(covSE.x, (y - m).reshape(-1))
-        return h.gpr_nlml(covSE.khyp(), want_grad=True)
+        return h.gpr_nlml(covSE.khyp(), want_grad=True, kind=covSE.KIND)
+
+    def _cov_class(self):
+        # GPr.py:59 hard-codes SquaredExponential; with one of the extension names the same kernel family as covFun
+        return COVARIANCE_FUNCTIONS.get(self.covFunName, SquaredExponential)
 
 
 class MeanFunction(object):
@@ -117,6 +121,7 @@ class CovarianceFunction(object):
 
 class SquaredExponential(CovarianceFunction):
     """GPr.py:90-110."""
+    KIND = 0            # radial function on the device (csrc/gpb_exp.cuh)
 
     def __init__(self, logHyp, x):
         CovarianceFunction.__init__(self, logHyp, x)
@@ -145,11 +150,25 @@ class SquaredExponential(CovarianceFunction):
         """GPr.py:99-103: full symmetric sn2*I + sf2*exp(-0.5*sqdist(x/M, x/M))."""
         h = _handle()
         h.set_train(self._points())
-        return h.kxx(self.khyp())
+        return h.kxx(self.khyp(), kind=self.KIND)
 
     def compute_Kxz_matrix(self, z):
         """GPr.py:105-110."""
         x, z = self._points(z)
         h = _handle()
         h.set_train(x)
-        return h.kxz(self.khyp(), z)
+        return h.kxz(self.khyp(), z, kind=self.KIND)
+
+
+class Matern32(SquaredExponential):
+    """sf2 (1 + sqrt(3) r) exp(-sqrt(3) r) + sn2 I with the ARD scaling and hyper-parameter layout of GPr.py:93-100.
+    Not in the reference (its string dispatch, GPr.py:28-32, knows only "SE"): SURVEY 8f rank 4."""
+    KIND = 1
+
+
+class Matern52(SquaredExponential):
+    """sf2 (1 + sqrt(5) r + 5 r^2 / 3) exp(-sqrt(5) r) + sn2 I; see Matern32."""
+    KIND = 2
+
+
+COVARIANCE_FUNCTIONS = {"SE": SquaredExponential, "Matern32": Matern32, "Matern52": Matern52}

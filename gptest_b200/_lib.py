@@ -119,6 +119,7 @@ class Handle:
             raise GpbError('gpb_create failed: %s' % self.lib.gpb_last_error(None).decode())
         self.h = hp
         self.device = device
+        self._cov_kind = 0
 
     def close(self):
         if getattr(self, 'h', None):
@@ -167,17 +168,27 @@ class Handle:
         self.check(self.lib.gpb_set_train(self.h, _dp(X), X.shape[0], X.shape[1], yp))
 
     # ---- covariance --------------------------------------------------------------------------
-    def kxx(self, khyp, flags=0):
+    # ``kind``: 0 squared exponential (the reference's only kernel, GPr.py:90-110), 1 Matern 3/2, 2 Matern 5/2.
+    # It is a handle option on the C side; every wrapper sets it, so the default is always the reference's kernel.
+    def _kind(self, kind):
+        if kind != self._cov_kind:
+            self.check(self.lib.gpb_set_option(self.h, b'cov_kind', int(kind)))
+            self._cov_kind = kind
+
+    def kxx(self, khyp, flags=0, kind=0):
+        self._kind(kind)
         khyp = as_f64(khyp)
         out = np.empty((self.n, self.n))
         self.check(self.lib.gpb_se_ard_kxx(self.h, _dp(khyp), out.ctypes.data_as(C.c_void_p), 0, flags))
         return out
 
-    def kxx_dev(self, khyp, dev_ptr, flags=0):
+    def kxx_dev(self, khyp, dev_ptr, flags=0, kind=0):
+        self._kind(kind)
         khyp = as_f64(khyp)
         self.check(self.lib.gpb_se_ard_kxx(self.h, _dp(khyp), C.c_void_p(dev_ptr), 1, flags))
 
-    def kxz(self, khyp, Z):
+    def kxz(self, khyp, Z, kind=0):
+        self._kind(kind)
         khyp = as_f64(khyp)
         Z = as_f64(Z)
         Z = Z.reshape(len(Z), -1)
@@ -193,7 +204,8 @@ class Handle:
         return out
 
     # ---- regression ----------------------------------------------------------------------------
-    def gpr_nlml(self, khyp, mean=0.0, want_grad=False):
+    def gpr_nlml(self, khyp, mean=0.0, want_grad=False, kind=0):
+        self._kind(kind)
         khyp = as_f64(khyp)
         val = C.c_double()
         info = C.c_int32()
@@ -204,7 +216,8 @@ class Handle:
             raise np.linalg.LinAlgError('Matrix is not positive definite (leading minor %d)' % info.value)
         return (val.value, grad) if want_grad else val.value
 
-    def gpr_predict(self, khyp, Z, mean=0.0):
+    def gpr_predict(self, khyp, Z, mean=0.0, kind=0):
+        self._kind(kind)
         khyp = as_f64(khyp)
         Z = as_f64(Z)
         Z = Z.reshape(len(Z), -1)
@@ -216,7 +229,8 @@ class Handle:
             raise np.linalg.LinAlgError('Matrix is not positive definite (leading minor %d)' % info.value)
         return fz, cov
 
-    def gpr_nlml_batched(self, khyp, mean=0.0, want_grad=False):
+    def gpr_nlml_batched(self, khyp, mean=0.0, want_grad=False, kind=0):
+        self._kind(kind)
         khyp = as_f64(khyp)
         B, p = khyp.shape
         val = np.empty(B)
@@ -227,7 +241,8 @@ class Handle:
         return (val, grad, info) if want_grad else (val, info)
 
     # ---- growing training set (GP_parameter_fit.py:61-63) --------------------------------------
-    def grow_begin(self, khyp, d, capacity, mean=0.0):
+    def grow_begin(self, khyp, d, capacity, mean=0.0, kind=0):
+        self._kind(kind)
         khyp = as_f64(khyp).reshape(-1)
         assert khyp.size == d + 2
         self.check(self.lib.gpb_gpr_grow_begin(self.h, _dp(khyp), int(d), float(mean), int(capacity)))

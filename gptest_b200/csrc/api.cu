@@ -91,6 +91,7 @@ void prep_train(gpb_handle* h, const Params& pr, int batch) {
 // K (lower tiles, identity padded) into the symmetric part of m
 void build_k_into(gpb_handle* h, FactorMat& m, const Params& pr, int mode, int clip) {
   SeArgs a{};
+  a.kind = h->cov_kind;
   a.rT = a.cT = h->XsT.as<double>();
   a.r_ld = a.c_ld = h->n_pad;
   a.r_sq = a.c_sq = h->sq.as<double>();
@@ -231,6 +232,10 @@ int gpb_set_option(gpb_handle* h, const char* name, int64_t value) {
   else if (!strcmp(name, "nb_switch4")) h->nb_switch4 = static_cast<int>(value);
   else if (!strcmp(name, "nb_switch2")) h->nb_switch2 = static_cast<int>(value);
   else if (!strcmp(name, "la_max_batch")) h->la_max_batch = static_cast<int>(value);
+  else if (!strcmp(name, "cov_kind")) {
+    if (value < 0 || value > 2) return -4;
+    h->cov_kind = static_cast<int>(value);
+  }
   else { h->err = std::string("unknown option ") + name; return -1; }
   return 0;
 }
@@ -270,6 +275,7 @@ int gpb_se_ard_kxx(gpb_handle* h, const double* khyp, double* K_out, int32_t out
   if (direct) { dst = K_out; ld = n; }
   else { h->A.ensure(static_cast<size_t>(np64) * np64 * 8); dst = h->A.as<double>(); ld = np64; }
   SeArgs a{};
+  a.kind = h->cov_kind;
   a.rT = a.cT = h->XsT.as<double>(); a.r_ld = a.c_ld = h->n_pad;
   a.r_sq = a.c_sq = h->sq.as<double>();
   a.n_rows_valid = a.n_cols_valid = n; a.d = h->d;
@@ -308,6 +314,7 @@ static int kxz_common(gpb_handle* h, const double* khyp, const double* Z, int64_
   prep_test(h, pr, Z, m, mp64);
   h->A.ensure(static_cast<size_t>(np64) * mp64 * 8);
   SeArgs a{};
+  a.kind = h->cov_kind;
   a.rT = h->XsT.as<double>(); a.r_ld = h->n_pad; a.r_sq = h->sq.as<double>(); a.n_rows_valid = n;
   a.cT = h->ZsT.as<double>(); a.c_ld = mp64; a.c_sq = h->zsq.as<double>(); a.n_cols_valid = m;
   a.d = h->d; a.out = h->A.as<double>(); a.ld = mp64; a.rows_pad = np64; a.cols_pad = mp64;
@@ -380,6 +387,7 @@ int gpb_gpr_predict(gpb_handle* h, const double* khyp, double mean, const double
   {
     // Kzx rows (GPr.py:46,49) appended below the y row
     SeArgs a{};
+    a.kind = h->cov_kind;
     a.rT = h->ZsT.as<double>(); a.r_ld = mp64; a.r_sq = h->zsq.as<double>(); a.n_rows_valid = mz;
     a.cT = h->XsT.as<double>(); a.c_ld = np; a.c_sq = h->sq.as<double>(); a.n_cols_valid = h->n;
     a.d = h->d; a.out = m.A + (np + 1) * m.ld; a.ld = m.ld; a.rows_pad = mp64; a.cols_pad = np;

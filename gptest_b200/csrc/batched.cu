@@ -82,6 +82,7 @@ extern "C" int gpb_gpr_nlml_batched(gpb_handle* h, const double* khyp, int64_t B
       launch_se_prep(h->X.as<double>(), h->n, d, ell, h->XsT.as<double>(), np, h->sq.as<double>(), bc, d,
                      static_cast<int64_t>(d) * np, np, h->s0);
       SeArgs a{};
+      a.kind = h->cov_kind;
       a.rT = a.cT = h->XsT.as<double>(); a.r_ld = a.c_ld = np;
       a.r_sq = a.c_sq = h->sq.as<double>();
       a.n_rows_valid = a.n_cols_valid = h->n;

@@ -59,6 +59,8 @@ struct gpb_handle {
   int nb_tiles = 0;              // 0 = choose from the remaining matrix size (see chol.cu)
   int nb_switch4 = 64, nb_switch2 = 24;   // remaining tile columns from which the block is 4 / 2 tiles wide
   int64_t batch_chunk = 0;       // 0 = auto
+  int cov_kind = 0;              // covariance of the regression paths: 0 squared exponential (GPr.py:90-110), 1 Matern 3/2,
+                                 // 2 Matern 5/2 (the Laplace paths stay squared exponential)
   int la_max_batch = 1 << 30;    // batches up to this size use the look-ahead schedule and adaptive widths
                                  // (measured: N=16384 B=4 47.5 vs 50.2 ms/fit, N=4096 B=8 1.08 vs 1.20; 1024x2048 neutral)
   int split_tiles = 1;           // big launches: 1 = 128x64 CTAs, two per SM (finer grain: the look-ahead panel

@@ -53,4 +53,34 @@ __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ t
   return s * __hiloint2double((m + 1023) << 20, 0);                      // exact scaling by 2^m
 }
 
+// Radial part of the stationary covariance functions, from x = -r^2/2 (r = scaled distance):
+//   KIND 0  squared exponential   exp(-r^2/2)                                  (GPr.py:102)
+//   KIND 1  Matern 3/2            (1 + a) exp(-a),            a = sqrt(3) r
+//   KIND 2  Matern 5/2            (1 + a + a^2/3) exp(-a),    a = sqrt(5) r
+// radial_dl is g(r) in  dk/dlog l_k = sf2 * g(r) * (x_ik - x_jk)^2 / l_k^2  (the ARD length-scale derivative):
+//   SE: exp(-r^2/2)     Matern 3/2: 3 exp(-a)     Matern 5/2: (5/3) (1 + a) exp(-a)
+template <int KIND>
+__device__ __forceinline__ double radial(double x, const double* __restrict__ tab) {
+  if (KIND == 0) return exp_tab(x, tab);
+  const double r = sqrt(fmax(-2.0 * x, 0.0));
+  if (KIND == 1) {
+    const double a = 1.7320508075688772 * r;
+    return (1.0 + a) * exp_tab(-a, tab);
+  }
+  const double a = 2.23606797749979 * r;
+  return fma(a, fma(a, 1.0 / 3.0, 1.0), 1.0) * exp_tab(-a, tab);
+}
+template <int KIND>
+__device__ __forceinline__ void radial_and_dl(double x, const double* __restrict__ tab, double& k, double& g) {
+  if (KIND == 0) { k = exp_tab(x, tab); g = k; return; }
+  const double r = sqrt(fmax(-2.0 * x, 0.0));
+  if (KIND == 1) {
+    const double a = 1.7320508075688772 * r, e = exp_tab(-a, tab);
+    k = (1.0 + a) * e; g = 3.0 * e; return;
+  }
+  const double a = 2.23606797749979 * r, e = exp_tab(-a, tab);
+  k = fma(a, fma(a, 1.0 / 3.0, 1.0), 1.0) * e;
+  g = (5.0 / 3.0) * (1.0 + a) * e;
+}
+
 }  // namespace gpb

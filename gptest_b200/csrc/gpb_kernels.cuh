@@ -80,6 +80,7 @@ struct SeArgs {
                                   // 2: rectangular (no noise term, pad = 0)
                                   // 3: rectangular, raw squared distances (no exp)
   int clip;                       // 1: clamp r^2 at 0 (GPy RBF semantics)
+  int kind;                       // radial function: 0 squared exponential, 1 Matern 3/2, 2 Matern 5/2 (gpb_exp.cuh)
 };
 void launch_se_build(const SeArgs& a, int batch, cudaStream_t st);
 

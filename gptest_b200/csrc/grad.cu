@@ -71,8 +71,10 @@ struct TraceArgs {
   int d;
   double* partial;                          // [batch][ntiles][d+2]
   int64_t ntiles;
+  int kind;                                 // radial function (gpb_exp.cuh)
 };
 
+template <int KIND>
 __global__ void __launch_bounds__(256) grad_trace_kernel(const TraceArgs p) {
   __shared__ double xr[GDC][GT];
   __shared__ double xc[GDC][GT];
@@ -125,13 +127,14 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const TraceArgs p) {
       double v = 0.0;
       if (r < p.n && cc < p.n) {
         const double r2 = (sq[r] + sq[cc]) - 2.0 * dot[a][c];
-        const double kse = sf2 * exp_tab(-0.5 * r2, etab);     // same exp as the assembly kernel
-        const double Q = Kinv[r * p.ld + cc] - al[r] * al[cc];
-        v = wgt * Q * kse;
-        if (r == cc) acc_sn += Q;
+        double kr, gr;
+        radial_and_dl<KIND>(-0.5 * r2, etab, kr, gr);         // same exp as the assembly kernel
+        const double Q = wgt * sf2 * (Kinv[r * p.ld + cc] - al[r] * al[cc]);
+        v = Q * gr;                                           // length-scale derivative weight (SE: gr == kr)
+        acc_sf += Q * kr;
+        if (r == cc) acc_sn += Kinv[r * p.ld + cc] - al[r] * al[cc];
       }
       q[a][c] = v;
-      acc_sf += v;
     }
   }
   double* out = p.partial + (static_cast<int64_t>(b) * p.ntiles + blockIdx.x) * (p.d + 2);
@@ -301,6 +304,7 @@ int gpr_nlml_grad_chunk(gpb_handle* h, const double* khyp, int64_t B, double mea
     launch_se_prep(h->X.as<double>(), h->n, d, ell, h->XsT.as<double>(), np, h->sq.as<double>(), bc, d,
                    static_cast<int64_t>(d) * np, np, h->s0);
     SeArgs a{};
+    a.kind = h->cov_kind;
     a.rT = a.cT = h->XsT.as<double>(); a.r_ld = a.c_ld = np;
     a.r_sq = a.c_sq = h->sq.as<double>();
     a.n_rows_valid = a.n_cols_valid = h->n;
@@ -331,7 +335,10 @@ int gpr_nlml_grad_chunk(gpb_handle* h, const double* khyp, int64_t B, double mea
     t.partial = h->aux1.as<double>(); t.ntiles = ntiles;
     {
       dim3 grid(static_cast<unsigned>(ntiles), bc);
-      grad_trace_kernel<<<grid, 256, 0, h->s0>>>(t);
+      t.kind = h->cov_kind;
+      if (t.kind == 1) grad_trace_kernel<1><<<grid, 256, 0, h->s0>>>(t);
+      else if (t.kind == 2) grad_trace_kernel<2><<<grid, 256, 0, h->s0>>>(t);
+      else grad_trace_kernel<0><<<grid, 256, 0, h->s0>>>(t);
       GPB_CUDA(cudaGetLastError());
       dim3 g2(P, bc);
       grad_reduce_kernel<<<g2, 256, 0, h->s0>>>(h->aux1.as<double>(), ntiles, P, res + bc);

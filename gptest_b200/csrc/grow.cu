@@ -25,7 +25,7 @@ constexpr int64_t PRED_ROWS = 2048;     // test points swept per pass
 
 struct GrowState {
   int64_t cap = 0, cap_pad = 0, n = 0;
-  int d = 0;
+  int d = 0, kind = 0;
   double mean = 0.0;
   DevBuf X, yc, XsT, sq, A, Dinv, diag, info, par, r, z, tmp, out;
   TileMaps mapA, mapD;
@@ -85,7 +85,7 @@ int gpb_gpr_grow_begin(gpb_handle* h, const double* khyp, int32_t d, double mean
   grow_release(h);
   GrowState* g = new GrowState;
   h->grow = g;
-  g->cap = capacity; g->cap_pad = round_up(capacity, TILE); g->d = d; g->mean = mean; g->n = 0;
+  g->cap = capacity; g->cap_pad = round_up(capacity, TILE); g->d = d; g->mean = mean; g->n = 0; g->kind = h->cov_kind;
   const int64_t cp = g->cap_pad, rows_alloc = cp + PRED_ROWS;
   g->X.ensure(static_cast<size_t>(capacity) * d * 8);
   g->yc.ensure(static_cast<size_t>(cp) * 8);
@@ -142,6 +142,7 @@ int gpb_gpr_grow_append(gpb_handle* h, const double* X_new, const double* y_new,
   ++h->launches;
   // rows [r0, np1) of K: left of r0 the plain cross-covariance, from r0 the symmetric block (noise, identity padding)
   SeArgs a{};
+  a.kind = g->kind;
   a.d = d; a.hyp_dev = hyp2; a.clip = 0; a.ld = cp;
   a.rT = g->XsT.as<double>() + r0; a.r_ld = cp; a.r_sq = g->sq.as<double>() + r0; a.n_rows_valid = n1 - r0;
   a.rows_pad = np1 - r0;
@@ -233,6 +234,7 @@ int gpb_gpr_grow_predict(gpb_handle* h, const double* Z, int64_t mz, double* fz,
     GPB_CUDA(cudaMemcpyAsync(h->Zd.p, Z + z0 * d, static_cast<size_t>(mc) * d * 8, cudaMemcpyHostToDevice, st));
     launch_se_prep(h->Zd.as<double>(), mc, d, ell, h->ZsT.as<double>(), mp64, h->zsq.as<double>(), 1, 0, 0, 0, st);
     SeArgs a{};                                           // Kzx rows (GPr.py:46,49) under the factor
+    a.kind = g->kind;
     a.rT = h->ZsT.as<double>(); a.r_ld = mp64; a.r_sq = h->zsq.as<double>(); a.n_rows_valid = mc;
     a.cT = g->XsT.as<double>(); a.c_ld = cp; a.c_sq = g->sq.as<double>(); a.n_cols_valid = n;
     a.d = d; a.out = A + cp * cp; a.ld = cp; a.rows_pad = mp64; a.cols_pad = np;

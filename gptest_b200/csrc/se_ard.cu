@@ -54,7 +54,7 @@ void launch_se_prep(const double* X, int64_t n, int d, const double* ell_dev, do
 }
 
 // MODE 0: symmetric, both triangles  1: symmetric, lower tiles only  2: rectangular  3: rectangular, raw r^2
-template <int MODE, int CLIP>
+template <int MODE, int CLIP, int KIND>
 __global__ void __launch_bounds__(256, 4) se_build_kernel(const SeArgs p) {
   __shared__ double xr[SDC][ST];
   __shared__ double xc[SDC][ST];
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256, 4) se_build_kernel(const SeArgs p) {
     for (int c = 0; c < 4; ++c) {
       double x = dot[a][c] - (hr[a] + hc[c]);
       if (CLIP) x = fmin(x, 0.0);                                    // r2 clipped at 0 (GPy RBF semantics)
-      val[a][c] = (MODE == 3) ? -2.0 * x : sf2 * exp_tab(x, etab);   // GPr.py:102 / :109 (mode 3: GPr.py:12 only)
+      val[a][c] = (MODE == 3) ? -2.0 * x : sf2 * radial<KIND>(x, etab);   // GPr.py:102 / :109 (mode 3: GPr.py:12 only)
     }
   if (diag_tile && ty == tx) {                                 // sn2 * eye: cells with a == c of the threads on the diagonal
 #pragma unroll
@@ -174,13 +174,16 @@ __global__ void __launch_bounds__(256, 4) se_build_kernel(const SeArgs p) {
 
 template <int MODE>
 static void launch_mode(const SeArgs& a, dim3 grid, cudaStream_t st) {
-  if (a.clip) se_build_kernel<MODE, 1><<<grid, 256, 0, st>>>(a);
-  else se_build_kernel<MODE, 0><<<grid, 256, 0, st>>>(a);
+  if (MODE < 3 && a.kind == 1) se_build_kernel<MODE, 1, 1><<<grid, 256, 0, st>>>(a);        // Matern: r^2 always clamped
+  else if (MODE < 3 && a.kind == 2) se_build_kernel<MODE, 1, 2><<<grid, 256, 0, st>>>(a);
+  else if (a.clip) se_build_kernel<MODE, 1, 0><<<grid, 256, 0, st>>>(a);
+  else se_build_kernel<MODE, 0, 0><<<grid, 256, 0, st>>>(a);
 }
 
 void launch_se_build(const SeArgs& a, int batch, cudaStream_t st) {
   const int64_t tr = a.rows_pad / ST, tcn = a.cols_pad / ST;
   GPB_REQUIRE(a.rows_pad % ST == 0 && a.cols_pad % ST == 0, "se_build: padded extents must be multiples of 64");
+  GPB_REQUIRE(a.kind >= 0 && a.kind <= 2, "se_build: unknown covariance kind");
   int64_t tiles = (a.mode >= 2) ? tr * tcn : tr * (tr + 1) / 2;
   if (tiles == 0) return;
   dim3 grid(static_cast<unsigned>(tiles), batch);

@@ -43,6 +43,8 @@ void* gpb_get_stream(gpb_handle* h);
 int gpb_destroy(gpb_handle* h);
 const char* gpb_last_error(gpb_handle* h);            /* h may be NULL: last create error */
 /* tunables: "lookahead" (0/1), "nb_tiles" (outer block = nb_tiles*128 columns: 1,2,4),
+ * "cov_kind" (covariance of the regression entry points: 0 squared exponential = GPr.py:90-110, the default;
+ * 1 Matern 3/2, 2 Matern 5/2 - same hyper-parameter layout and ARD scaling; extension),
  * "batch_chunk" (problems resident at once in the batched path), "la_max_batch" (largest batch that
  * uses the look-ahead schedule; default: all), and the schedule knobs "nb_switch4", "nb_switch2",
  * "split_tiles", "small_tile_threshold", "persistent_waves", "stagger" (see gpb_context.cuh).

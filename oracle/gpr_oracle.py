@@ -145,3 +145,76 @@ def nlml_grad(hyp, x, y):
     g[d] = 0.5 * np.sum(Q * (2.0 * Kse))
     g[d + 1] = 0.5 * np.trace(Q) * 2.0 * sn2
     return g
+
+
+# ----------------------------------------------------------------------------------------
+# Other stationary covariance functions behind the reference's string dispatch (GPr.py:28-32 selects by name
+# and knows only "SE").  SURVEY 8f rank 4 - NOT in the reference; textbook forms (Rasmussen & Williams eq. 4.17)
+# with the same hyper-parameter layout [log l_1..l_D, log sf, log sn] and the same ARD scaling as GPr.py:100.
+# ----------------------------------------------------------------------------------------
+KINDS = {'SE': 0, 'Matern32': 1, 'Matern52': 2}
+
+
+def radial(kind, r2):
+    """k(r)/sf2 and g(r) with dk/dlog l_k = sf2 * g(r) * (scaled difference in dimension k)^2."""
+    r2 = np.maximum(r2, 0.0)
+    if kind == 'SE':
+        k = np.exp(-0.5 * r2)
+        return k, k
+    r = np.sqrt(r2)
+    if kind == 'Matern32':
+        a = np.sqrt(3.0) * r
+        e = np.exp(-a)
+        return (1 + a) * e, 3.0 * e
+    if kind == 'Matern52':
+        a = np.sqrt(5.0) * r
+        e = np.exp(-a)
+        return (1 + a + a * a / 3.0) * e, (5.0 / 3.0) * (1 + a) * e
+    raise ValueError(kind)
+
+
+def kxx_kind(log_hyp, x, kind='SE'):
+    x = np.asarray(x, dtype=float).reshape(len(x), -1)
+    ell, sf2, sn2 = split_hyp(log_hyp)
+    xs = x / ell
+    return sf2 * radial(kind, sqdist_expanded(xs, xs))[0] + sn2 * np.eye(len(x))
+
+
+def kxz_kind(log_hyp, x, z, kind='SE'):
+    x = np.asarray(x, dtype=float).reshape(len(x), -1)
+    z = np.asarray(z, dtype=float).reshape(len(z), -1)
+    ell, sf2, _ = split_hyp(log_hyp)
+    return sf2 * radial(kind, sqdist_expanded(x / ell, z / ell))[0]
+
+
+def nlml_kind(log_hyp, x, y, kind='SE', want_grad=False):
+    from scipy.linalg import cho_solve
+    x = np.asarray(x, dtype=float).reshape(len(x), -1)
+    yv = np.asarray(y, dtype=float).reshape(-1)
+    ell, sf2, sn2 = split_hyp(log_hyp)
+    n, d = x.shape
+    xs = x / ell
+    kr, gr = radial(kind, sqdist_expanded(xs, xs))
+    K = sf2 * kr + sn2 * np.eye(n)
+    L = np.linalg.cholesky(K)
+    alpha = cho_solve((L, True), yv)
+    val = 0.5 * yv @ alpha + np.sum(np.log(np.diag(L))) + n * np.log(2 * np.pi) / 2
+    if not want_grad:
+        return val
+    Q = cho_solve((L, True), np.eye(n)) - np.outer(alpha, alpha)
+    g = np.empty(d + 2)
+    for k in range(d):
+        g[k] = 0.5 * np.sum(Q * sf2 * gr * (xs[:, k:k + 1] - xs[:, k:k + 1].T) ** 2)
+    g[d] = 0.5 * np.sum(Q * 2.0 * sf2 * kr)
+    g[d + 1] = 0.5 * np.trace(Q) * 2.0 * sn2
+    return val, g
+
+
+def predict_kind(log_hyp, x, y, z, kind='SE'):
+    from scipy.linalg import cho_solve, solve_triangular
+    K = kxx_kind(log_hyp, x, kind)
+    Ks = kxz_kind(log_hyp, x, z, kind)
+    L = np.linalg.cholesky(K)
+    alpha = cho_solve((L, True), np.asarray(y, dtype=float).reshape(-1))
+    V = solve_triangular(L, Ks, lower=True)
+    return Ks.T @ alpha, split_hyp(log_hyp)[1] - np.sum(V * V, axis=0)

@@ -120,3 +120,56 @@ def test_argument_errors(handle):
     with pytest.raises(GpbError):
         handle.pref_laplace(np.array([[0, 10]], dtype=np.int64), np.ones((1, 1)), np.array([1.0, 1.0, 1.0]),
                             sigma=1.0, delta_f=1e-6, max_iter=10)      # item index out of range
+
+
+# ---- other covariance functions behind the string dispatch (not in the reference) -----------
+@pytest.mark.parametrize('name', ['Matern32', 'Matern52'])
+@pytest.mark.parametrize('n,d', [(90, 1), (700, 3), (1100, 8)])
+def test_matern_paths_match_oracle(handle, name, n, d):
+    kind = gpr_oracle.KINDS[name]
+    rng = np.random.default_rng(n + d)
+    X = rng.random((n, d))
+    y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(n)
+    Z = rng.random((77, d))
+    lh = np.log([0.7] * d + [1.3, 0.2])
+    kh = natural(lh)
+    handle.set_train(X, y)
+    K = handle.kxx(kh, kind=kind)
+    assert np.abs(K - gpr_oracle.kxx_kind(lh, X, name)).max() < 1e-12
+    assert np.abs(handle.kxz(kh, Z, kind=kind) - gpr_oracle.kxz_kind(lh, X, Z, name)).max() < 1e-12
+    v, g = handle.gpr_nlml(kh, want_grad=True, kind=kind)
+    rv, rg = gpr_oracle.nlml_kind(lh, X, y, name, want_grad=True)
+    assert abs(v - rv) <= 1e-8 * max(1.0, abs(rv))
+    assert np.abs(g - rg).max() <= 1e-7 * max(1.0, np.abs(rg).max())
+    assert abs(handle.gpr_nlml(kh, kind=kind) - rv) <= 1e-8 * max(1.0, abs(rv))
+    fz, cov = handle.gpr_predict(kh, Z, kind=kind)
+    rf, rc = gpr_oracle.predict_kind(lh, X, y, Z, name)
+    assert np.abs(fz - rf).max() <= 1e-9 * max(1.0, np.abs(rf).max()) and np.abs(cov - rc).max() <= 1e-9
+    vals, info = handle.gpr_nlml_batched(np.array([kh, kh * 1.1]), kind=kind)
+    assert abs(vals[0] - rv) <= 1e-8 * max(1.0, abs(rv)) and not info.any()
+    # the default stays the reference's kernel
+    assert abs(handle.gpr_nlml(kh) - gpr_oracle.nlml_chol(lh, X, y)) <= 1e-8 * max(1.0, abs(rv))
+
+
+def test_matern_dropin_names_and_growing_set(handle):
+    from gptest_b200 import GPr
+    rng = np.random.default_rng(8)
+    X = rng.random((150, 2))
+    y = np.cos(3 * X[:, 0]) + 0.1 * rng.standard_normal(150)
+    Z = rng.random((20, 2))
+    lh = np.log([0.5, 0.8, 1.0, 0.15])
+    gp = GPr.GaussianProcess(lh, 0, 0, "Matern52", "zero", "zero", X, y)
+    assert isinstance(gp.covFun, GPr.Matern52)
+    v = gp.compute_likelihood(lh)
+    assert v.shape == (1, 1) and abs(v[0, 0] - gpr_oracle.nlml_kind(lh, X, y, 'Matern52')) <= 1e-8 * abs(v[0, 0])
+    fz, cov = gp.compute_prediction(Z)
+    rf, rc = gpr_oracle.predict_kind(lh, X, y, Z, 'Matern52')
+    assert np.abs(fz - rf).max() < 1e-9 and np.abs(cov - rc).max() < 1e-9
+    assert GPr.GaussianProcess(lh, 0, 0, "nope", "zero", "zero", X, y).covFun == []       # GPr.py:31-32
+    handle.grow_begin(natural(lh), 2, capacity=150, kind=1)
+    handle.grow_append(X[:100], y[:100])
+    v2 = handle.grow_append(X[100:], y[100:])
+    assert abs(v2 - gpr_oracle.nlml_kind(lh, X, y, 'Matern32')) <= 1e-8 * abs(v2)
+    fz, cov = handle.grow_predict(Z)
+    rf, rc = gpr_oracle.predict_kind(lh, X, y, Z, 'Matern32')
+    assert np.abs(fz - rf).max() < 1e-9 and np.abs(cov - rc).max() < 1e-9
