@@ -229,6 +229,7 @@ int gpb_set_option(gpb_handle* h, const char* name, int64_t value) {
   else if (!strcmp(name, "split_tiles")) h->split_tiles = value != 0;
   else if (!strcmp(name, "persistent_waves")) dmma_gemm_set_persistent(static_cast<int>(value));
   else if (!strcmp(name, "stagger")) dmma_gemm_set_stagger(static_cast<int>(value));
+  else if (!strcmp(name, "pdl")) dmma_gemm_set_pdl(static_cast<int>(value));
   else if (!strcmp(name, "nb_switch4")) h->nb_switch4 = static_cast<int>(value);
   else if (!strcmp(name, "nb_switch2")) h->nb_switch2 = static_cast<int>(value);
   else if (!strcmp(name, "la_max_batch")) h->la_max_batch = static_cast<int>(value);

@@ -86,6 +86,7 @@ struct Sweep {
   int nt, R;
   int x0 = 0, xn = 0;     // non-factor mode: tile rows [x0, x0 + xn) are swept
   bool grow = false;      // identity right-hand sides: tile row x0 + q is zero left of column q
+  bool pdl = false;       // small launches of this sweep chain with programmatic dependent launch
 
   // last tile row (exclusive) that can be non-zero once tile column k has been processed
   int r_at(int k) const {
@@ -100,6 +101,7 @@ struct Sweep {
     a.c_batch_stride = m.batch_stride;
     a.rows_total = static_cast<int>(m.rows_total);
     a.R = r_at(k);
+    a.pdl = pdl;
     if (factor) {
       a.tri = 1;
     } else {
@@ -159,7 +161,7 @@ struct Sweep {
         TilePotrfArgs t{};
         t.A = m.A; t.lda = m.ld; t.a_batch_stride = m.batch_stride; t.k = k;
         t.Dinv = m.Dinv; t.d_batch_stride = m.dinv_bs;
-        t.diag = m.diag; t.diag_batch_stride = m.diag_bs; t.info = m.info;
+        t.diag = m.diag; t.diag_batch_stride = m.diag_bs; t.info = m.info; t.pdl = pdl;
         launch_tile_potrf_inv(t, m.batch, st);
         ++h->launches;
       }
@@ -207,6 +209,10 @@ void chol_sweep(gpb_handle* h, FactorMat& m, const SweepPlan& plan) {
   };
   // without a symmetric part to factor there is no panel critical path: plain order
   const bool la = h->lookahead && factor && m.batch <= h->la_max_batch && nt > width_at(0);
+  // Programmatic dependent launch pays where the chain of small kernels IS the run time (small matrices, thin
+  // sweeps: +3 % at N <= 2048, thin appends); next to a look-ahead trailing update the early-resident waiters
+  // take SM slots from it (measured: -4 % at N = 8192 / 16384), so it stays off there.
+  s.pdl = !la || nt <= 24;
 
   if (!la) {
     for (int kb = 0; kb < nt;) {

@@ -68,6 +68,7 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * STAGE);
   uint64_t* empty = full + GEMM_STAGES;
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int per_batch = p.ntiles * NSPLIT;   // CTA-tiles per batch entry
@@ -91,6 +92,7 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_wait();                                // operands and C come from the preceding kernels of the stream
 
   // ---------------- producer state (only thread 0 uses it) ----------------
   const bool producer = (threadIdx.x == 0);
@@ -263,6 +265,8 @@ constexpr int smem_bytes(int bm, int bn) { return GEMM_STAGES * (bm + bn) * GEMM
 static int g_num_sms = 148;
 static int g_persistent_waves = 0;
 void dmma_gemm_set_persistent(int waves) { g_persistent_waves = waves < 0 ? 0 : waves; }
+int g_pdl = 1;
+void dmma_gemm_set_pdl(int mode) { g_pdl = mode < 0 ? 0 : mode; }
 static int g_stagger = 1;
 void dmma_gemm_set_stagger(int on) { g_stagger = on != 0; }
 
@@ -307,19 +311,27 @@ void launch_dmma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmArgs
     }
     return dim3(static_cast<unsigned>(gx), 1, 1);
   };
+  // programmatic dependent launch for the launches that fit the machine at once (the dependent chains of the panel
+  // and of the sweeps); a multi-wave trailing update gains nothing and its early-resident successor would sit in
+  // slots the look-ahead panel wants
+  const bool small = static_cast<int64_t>(ntiles) * a.nbatch <= 2LL * g_num_sms;
+  const bool pdl = g_pdl == 2 || (g_pdl == 1 && small && a.pdl != 0);
   if (tile == 128) {
-    dmma_gemm_nt_kernel<128, 128, 2, 4, 1><<<grid_for(ntiles, 1), 8 * 32, smem_bytes(128, 128), st>>>(mapA, mapB, a);
+    launch_chain(dmma_gemm_nt_kernel<128, 128, 2, 4, 1>, grid_for(ntiles, 1), dim3(8 * 32), smem_bytes(128, 128), st, pdl,
+                 mapA, mapB, a);
   } else if (tile == 12864) {
     // region in 128-tiles, each cut into two 128 x 64 CTA-tiles; two CTAs share an SM
     // (mapA with 128-row boxes, mapB with 64-row boxes)
-    dmma_gemm_nt_kernel<128, 64, 2, 2, 2><<<grid_for(2 * ntiles, 2), 4 * 32, smem_bytes(128, 64), st>>>(mapA, mapB, a);
+    launch_chain(dmma_gemm_nt_kernel<128, 64, 2, 2, 2>, grid_for(2 * ntiles, 2), dim3(4 * 32), smem_bytes(128, 64), st, pdl,
+                 mapA, mapB, a);
   } else if (tile == 64) {
-    dmma_gemm_nt_kernel<64, 64, 2, 2, 3><<<grid_for(ntiles, 3), 4 * 32, smem_bytes(64, 64), st>>>(mapA, mapB, a);
+    launch_chain(dmma_gemm_nt_kernel<64, 64, 2, 2, 3>, grid_for(ntiles, 3), dim3(4 * 32), smem_bytes(64, 64), st, pdl,
+                 mapA, mapB, a);
   } else {
     // 64 x 128: rows in units of 64, columns in units of 128 (mapA with 64-row boxes, mapB with 128-row boxes)
-    dmma_gemm_nt_kernel<64, 128, 2, 2, 2><<<grid_for(ntiles, 2), 4 * 32, smem_bytes(64, 128), st>>>(mapA, mapB, a);
+    launch_chain(dmma_gemm_nt_kernel<64, 128, 2, 2, 2>, grid_for(ntiles, 2), dim3(4 * 32), smem_bytes(64, 128), st, pdl,
+                 mapA, mapB, a);
   }
-  GPB_CUDA(cudaGetLastError());
 }
 
 // ---------------------------------------------------------------------------------------

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
 #error "libgpb200 is written for sm_100a (B200) only"
@@ -98,5 +99,29 @@ struct Error {
   } while (0)
 
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// ---- programmatic dependent launch -------------------------------------------------------
+// The panel of the factorisation and the substitution sweeps are chains of small dependent kernels
+// (tile_potrf -> TRSM -> update -> tile_potrf ...).  Launched with the programmatic-serialisation attribute, the
+// next kernel of the chain becomes resident while its predecessor drains: launch latency and the prologue
+// (barrier initialisation, table staging) leave the critical path.  Every kernel launched this way calls
+// pdl_trigger() first and pdl_wait() before its first access to global memory; both are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+extern int g_pdl;       // 0: off  1: the small launches of dependent chains (default)  2: every launch (dmma_gemm.cu)
+
+template <class... KArgs, class... Args>
+inline void launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                         Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  GPB_CUDA(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
+}
 
 }  // namespace gpb

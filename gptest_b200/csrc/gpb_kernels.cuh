@@ -28,6 +28,7 @@ struct GemmArgs {
   int nbatch;               // batch entries (filled by the launcher); work list = nbatch x tiles
   int num_sms;              // filled by the launcher
   long long stagger_clk;    // > 0: delay (SM clocks) of the second resident CTA per SM in the first wave
+  int pdl;                  // launch with programmatic stream serialisation if the launch is small (see gpb_common.cuh)
 };
 int gemm_region_tiles(const GemmArgs& a);       // host: number of tiles of the region
 // one tensor map per tile edge: the TMA box height is part of the map
@@ -41,6 +42,7 @@ void launch_dmma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmArgs
 GemmArgs gemm_args_to_64(const GemmArgs& a);
 void dmma_gemm_init();                           // sets the dynamic smem attribute once
 void dmma_gemm_set_persistent(int waves);        // 0 (default): one CTA per tile; n: persistent grid of n waves
+void dmma_gemm_set_pdl(int mode);               // programmatic dependent launch: 0 off, 1 small launches (default), 2 all
 void dmma_gemm_set_stagger(int on);              // 1 (default): phase-shift co-resident CTAs of the 2-per-SM variants
 
 // ---------------------------------------------------------------------------------------
@@ -56,6 +58,7 @@ struct TilePotrfArgs {
   double* diag;             // per batch: n_pad doubles
   int64_t diag_batch_stride;
   int* info;                // per batch: first failing pivot (1-based global index), 0 = ok
+  int pdl;                  // launch with programmatic stream serialisation
 };
 void launch_tile_potrf_inv(TilePotrfArgs a, int batch, cudaStream_t st);
 void tile_potrf_init();

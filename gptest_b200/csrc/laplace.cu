@@ -119,6 +119,8 @@ __global__ void __launch_bounds__(256) trsv_lt_step_kernel(const double* __restr
   __shared__ double xk[TILE];
   __shared__ double part[256];
   const int t = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();                                    // r comes from the previous step
   if (t < TILE) rk[t] = r[k * TILE + t];
   __syncthreads();
   {
@@ -169,8 +171,7 @@ void trsv_lt(gpb_handle* h, const FactorMat& m, double* r, double* x) {
   const int nt = static_cast<int>(m.n_pad / TILE);
   for (int k = nt - 1; k >= 0; --k) {
     const int blocks = k == 0 ? 1 : 2 * k;
-    trsv_lt_step_kernel<<<blocks, 256, 0, h->s0>>>(m.A, m.ld, m.Dinv, k, r, x);
-    GPB_CUDA(cudaGetLastError());
+    launch_chain(trsv_lt_step_kernel, dim3(blocks), dim3(256), 0, h->s0, g_pdl != 0, m.A, m.ld, m.Dinv, k, r, x);
     ++h->launches;
   }
 }

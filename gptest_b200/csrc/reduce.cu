@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(256) trsv_l_step_kernel(const double* __restri
   __shared__ __align__(32) double xk[TILE];
   __shared__ double part[256];
   const int t = threadIdx.x, b = blockIdx.y;
+  pdl_trigger();
+  pdl_wait();                                    // r comes from the previous step
   double* rb = r + b * r_bs;
   if (t < TILE) rk[t] = rb[k * TILE + t];
   __syncthreads();
@@ -152,8 +154,7 @@ void launch_trsv_l(const double* L, int64_t ld, int64_t l_bs, const double* Dinv
   for (int k = k_begin; k < nt; ++k) {
     const int64_t below = n_pad - static_cast<int64_t>(k + 1) * TILE;
     dim3 grid(static_cast<unsigned>(below > 0 ? (below + 63) / 64 : 1), batch);
-    trsv_l_step_kernel<<<grid, 256, 0, st>>>(L, ld, l_bs, Dinv, d_bs, k, n_pad, r, r_bs, x, x_bs);
-    GPB_CUDA(cudaGetLastError());
+    launch_chain(trsv_l_step_kernel, grid, dim3(256), 0, st, g_pdl != 0, L, ld, l_bs, Dinv, d_bs, k, n_pad, r, r_bs, x, x_bs);
   }
 }
 

@@ -101,7 +101,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tile_potrf_inv_kernel(const Til
   const int batch = blockIdx.x;
   double* Ab = p.A + batch * p.a_batch_stride + static_cast<int64_t>(p.k) * TILE * p.lda + p.k * TILE;
 
+  pdl_trigger();
   if (t == 0) fail = TILE;
+  pdl_wait();                                    // the tile was updated by the preceding kernels of the stream
   double c[8][8], dg[8];
 #pragma unroll
   for (int a = 0; a < 8; ++a)
@@ -151,8 +153,7 @@ void tile_potrf_init() {
 }
 
 void launch_tile_potrf_inv(TilePotrfArgs a, int batch, cudaStream_t st) {
-  tile_potrf_inv_kernel<<<batch, TP_THREADS, TP_SMEM, st>>>(a);
-  GPB_CUDA(cudaGetLastError());
+  launch_chain(tile_potrf_inv_kernel, dim3(batch), dim3(TP_THREADS), TP_SMEM, st, g_pdl != 0 && a.pdl != 0, a);
 }
 
 }  // namespace gpb
