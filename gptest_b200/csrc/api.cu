@@ -12,7 +12,7 @@ static std::string g_create_error;
 
 cudaEvent_t gpb_handle::next_event() {
   if (ev_pool.empty()) {
-    ev_pool.resize(64);
+    ev_pool.resize(256);
     for (auto& e : ev_pool) GPB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   cudaEvent_t e = ev_pool[ev_next];
@@ -209,6 +209,7 @@ int gpb_destroy(gpb_handle* h) {
   cudaDeviceSynchronize();
   if (h->own_s0 && h->s0) cudaStreamDestroy(h->s0);
   if (h->s1) cudaStreamDestroy(h->s1);
+  for (auto s : h->su) cudaStreamDestroy(s);
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   for (auto e : h->tev) if (e) cudaEventDestroy(e);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -230,8 +231,12 @@ int gpb_set_option(gpb_handle* h, const char* name, int64_t value) {
   else if (!strcmp(name, "persistent_waves")) dmma_gemm_set_persistent(static_cast<int>(value));
   else if (!strcmp(name, "stagger")) dmma_gemm_set_stagger(static_cast<int>(value));
   else if (!strcmp(name, "pdl")) dmma_gemm_set_pdl(static_cast<int>(value));
+  else if (!strcmp(name, "dag_streams")) h->dag_streams = static_cast<int>(value < 0 ? 0 : (value > 16 ? 16 : value));
+  else if (!strcmp(name, "dag_min_tiles")) h->dag_min_tiles = static_cast<int>(value);
+  else if (!strcmp(name, "dag_big_tiles")) h->dag_big_tiles = static_cast<int>(value);
   else if (!strcmp(name, "nb_switch4")) h->nb_switch4 = static_cast<int>(value);
   else if (!strcmp(name, "nb_switch2")) h->nb_switch2 = static_cast<int>(value);
+  else if (!strcmp(name, "nb_switch8")) h->nb_switch8 = static_cast<int>(value);
   else if (!strcmp(name, "la_max_batch")) h->la_max_batch = static_cast<int>(value);
   else if (!strcmp(name, "cov_kind")) {
     if (value < 0 || value > 2) return -4;

@@ -87,6 +87,7 @@ struct Sweep {
   int x0 = 0, xn = 0;     // non-factor mode: tile rows [x0, x0 + xn) are swept
   bool grow = false;      // identity right-hand sides: tile row x0 + q is zero left of column q
   bool pdl = false;       // small launches of this sweep chain with programmatic dependent launch
+  bool big_tiles = false; // chunked schedule: the launch is small but shares the machine with others - keep the big tiles
 
   // last tile row (exclusive) that can be non-zero once tile column k has been processed
   int r_at(int k) const {
@@ -102,6 +103,7 @@ struct Sweep {
     a.rows_total = static_cast<int>(m.rows_total);
     a.R = r_at(k);
     a.pdl = pdl;
+    a.no_stagger = big_tiles;
     if (factor) {
       a.tri = 1;
     } else {
@@ -114,7 +116,7 @@ struct Sweep {
   void launch(const GemmArgs& a, const TileMaps& ma, const TileMaps& mb, cudaStream_t st) {
     const int n128 = gemm_region_tiles(a);
     if (n128 <= 0) return;
-    if (static_cast<int64_t>(n128) * m.batch < h->small_tile_threshold) {
+    if (!big_tiles && static_cast<int64_t>(n128) * m.batch < h->small_tile_threshold) {
       launch_dmma_gemm(ma.m64, mb.m64, gemm_args_to_64(a), m.batch, st, 64);
     } else if (h->split_tiles) {
       launch_dmma_gemm(ma.m128, mb.m64, a, m.batch, st, 12864);
@@ -205,6 +207,7 @@ void chol_sweep(gpb_handle* h, FactorMat& m, const SweepPlan& plan) {
     // would behind a single matrix sqrt(batch) times larger
     int rem = nt - kb;
     if (m.batch > 1) rem = static_cast<int>(rem * sqrt(static_cast<double>(m.batch)));
+    if (h->nb_switch8 > 0 && rem >= h->nb_switch8) return 8;
     return rem >= h->nb_switch4 ? 4 : (rem >= h->nb_switch2 ? 2 : 1);
   };
   // without a symmetric part to factor there is no panel critical path: plain order
@@ -227,7 +230,59 @@ void chol_sweep(gpb_handle* h, FactorMat& m, const SweepPlan& plan) {
 
   int kb = 0;
   int kend = width_at(0) < nt ? width_at(0) : nt;
+
+  // ---- chunked schedule while the block is 4 tiles wide ------------------------------------------------
+  // One launch per step serialises whole trailing updates: every launch ends in a partly filled wave, and step
+  // s+1 cannot start a single tile before the last tile of step s is done.  Tiles of different column chunks are
+  // independent, so here the update of step s is issued as chunks of 4 tile columns, chunk c always on stream
+  // su[c % S]: the in-order stream gives "step s before step s+1" per chunk for free, one event per step makes
+  // the panel visible to the update streams, one event hands the next panel's chunk to the panel stream.  CTAs of
+  // several launches share the machine, so partial waves fill up and the panel chain runs ahead as far as its own
+  // chunk allows.  Same kernels, same per-tile order of operations: results are bitwise identical.
+  const int S = h->dag_streams;
+  const bool dag = S > 0 && m.batch == 1 && h->nb_tiles == 0 && nt >= h->dag_min_tiles;
   s.panel(0, kend, h->s0);
+  // one phase per block width (8, then 4): chunk -> stream is fixed inside a phase, phases are separated by a join
+  while (dag && kend < nt && width_at(kend) >= 4) {
+    const int CW = width_at(kend);
+    while (static_cast<int>(h->su.size()) < S) {
+      cudaStream_t st;
+      GPB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      h->su.push_back(st);
+    }
+    cudaEvent_t P = h->next_event();                       // panel [kb, kend) is done on s0
+    GPB_CUDA(cudaEventRecord(P, h->s0));
+    GPB_CUDA(cudaStreamWaitEvent(h->s1, P, 0));
+    while (kend < nt && width_at(kend) == CW) {
+      const int nend = kend + CW < nt ? kend + CW : nt;
+      cudaEvent_t Pn = P;
+      for (int i = 0; i < S; ++i) GPB_CUDA(cudaStreamWaitEvent(h->su[i], P, 0));
+      for (int c = kend; c < nt; c += CW) {
+        cudaStream_t st = h->su[(c / CW) % S];
+        s.big_tiles = h->dag_big_tiles != 0;
+        s.update(c, c + CW < nt ? c + CW : nt, kb, kend, st);
+        s.big_tiles = false;
+        if (c == kend) {                                   // the next panel's own chunk: hand it to the panel stream
+          cudaEvent_t U = h->next_event();
+          GPB_CUDA(cudaEventRecord(U, st));
+          GPB_CUDA(cudaStreamWaitEvent(h->s1, U, 0));
+          s.panel(kend, nend, h->s1);
+          Pn = h->next_event();
+          GPB_CUDA(cudaEventRecord(Pn, h->s1));
+        }
+      }
+      P = Pn;
+      kb = kend;
+      kend = nend;
+    }
+    // join: everything issued so far becomes visible to the handle's stream
+    GPB_CUDA(cudaStreamWaitEvent(h->s0, P, 0));
+    for (int i = 0; i < S; ++i) {
+      cudaEvent_t e = h->next_event();
+      GPB_CUDA(cudaEventRecord(e, h->su[i]));
+      GPB_CUDA(cudaStreamWaitEvent(h->s0, e, 0));
+    }
+  }
   while (kend < nt) {
     const int nbn = width_at(kend);
     const int nend = kend + nbn < nt ? kend + nbn : nt;

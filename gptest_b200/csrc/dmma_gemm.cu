@@ -300,7 +300,7 @@ void launch_dmma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmArgs
   {
     // half of the time a CTA-tile takes when two CTAs share the FP64 tensor pipe: nk slabs x 2048 clocks
     const long long nk = a.k_from_row ? (a.k_end / GEMM_KB) / 2 : a.nk;
-    a.stagger_clk = (g_stagger && static_cast<int64_t>(ntiles) * a.nbatch >= 2LL * g_num_sms) ? nk * 2048 : 0;
+    a.stagger_clk = (g_stagger && !a.no_stagger && static_cast<int64_t>(ntiles) * a.nbatch >= 2LL * g_num_sms) ? nk * 2048 : 0;
   }
   auto grid_for = [&](int cta_tiles, int per_sm) {
     const int64_t work = static_cast<int64_t>(cta_tiles) * a.nbatch;

@@ -51,14 +51,21 @@ struct gpb_handle {
   cudaStream_t s0 = nullptr;     // the handle's stream (all results are ordered on it)
   bool own_s0 = false;
   cudaStream_t s1 = nullptr;     // high-priority side stream for the look-ahead panel
+  std::vector<cudaStream_t> su;  // update streams of the chunked schedule (created on first use)
   std::string err;
   int64_t launches = 0;
 
   // options
   int lookahead = 1;
   int nb_tiles = 0;              // 0 = choose from the remaining matrix size (see chol.cu)
+  int nb_switch8 = 96;           // > 0: blocks of 8 tiles (K = 1024) while at least this many tile columns remain
+                                 // (N = 16384: 48.15 vs 48.5 ms with the chunked schedule, profiles/r01_dag_ab.json)
   int nb_switch4 = 64, nb_switch2 = 24;   // remaining tile columns from which the block is 4 / 2 tiles wide
   int64_t batch_chunk = 0;       // 0 = auto
+  int dag_streams = 4;           // > 0: while the block is 4 tiles wide, the trailing update is issued as column chunks
+                                 // on this many streams, ordered by events only (see chol.cu); 0 = one launch per step
+  int dag_big_tiles = 1;         // chunk updates keep the 128-row tiles although each launch is small
+  int dag_min_tiles = 72;        // matrices with fewer tile columns keep the one-launch schedule
   int cov_kind = 0;              // covariance of the regression paths: 0 squared exponential (GPr.py:90-110), 1 Matern 3/2,
                                  // 2 Matern 5/2 (the Laplace paths stay squared exponential)
   int la_max_batch = 1 << 30;    // batches up to this size use the look-ahead schedule and adaptive widths

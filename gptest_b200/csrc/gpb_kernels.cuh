@@ -29,6 +29,7 @@ struct GemmArgs {
   int num_sms;              // filled by the launcher
   long long stagger_clk;    // > 0: delay (SM clocks) of the second resident CTA per SM in the first wave
   int pdl;                  // launch with programmatic stream serialisation if the launch is small (see gpb_common.cuh)
+  int no_stagger;           // chunked schedule: CTAs of several launches share the SMs and dephase by themselves
 };
 int gemm_region_tiles(const GemmArgs& a);       // host: number of tiles of the region
 // one tensor map per tile edge: the TMA box height is part of the map
