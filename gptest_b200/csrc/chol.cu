@@ -243,7 +243,7 @@ void chol_sweep(gpb_handle* h, FactorMat& m, const SweepPlan& plan) {
   const bool dag = S > 0 && m.batch == 1 && h->nb_tiles == 0 && nt >= h->dag_min_tiles;
   s.panel(0, kend, h->s0);
   // one phase per block width (8, then 4): chunk -> stream is fixed inside a phase, phases are separated by a join
-  while (dag && kend < nt && width_at(kend) >= 4) {
+  while (dag && kend < nt && width_at(kend) >= h->dag_min_width) {
     const int CW = width_at(kend);
     while (static_cast<int>(h->su.size()) < S) {
       cudaStream_t st;

@@ -64,6 +64,7 @@ struct gpb_handle {
   int64_t batch_chunk = 0;       // 0 = auto
   int dag_streams = 4;           // > 0: while the block is 4 tiles wide, the trailing update is issued as column chunks
                                  // on this many streams, ordered by events only (see chol.cu); 0 = one launch per step
+  int dag_min_width = 4;         // narrowest block (tiles) that still uses the chunked schedule
   int dag_big_tiles = 1;         // chunk updates keep the 128-row tiles although each launch is small
   int dag_min_tiles = 72;        // matrices with fewer tile columns keep the one-launch schedule
   int cov_kind = 0;              // covariance of the regression paths: 0 squared exponential (GPr.py:90-110), 1 Matern 3/2,

@@ -87,6 +87,40 @@ def test_potrf_lookahead_and_block_width_are_bitwise_equivalent(handle):
         assert np.abs(o - outs[0]).max() < 1e-12
 
 
+def test_chunked_schedule_and_dependent_launch_are_bitwise_equivalent(handle):
+    """The chunked multi-stream trailing update (chol.cu) and programmatic dependent launch only reorder launches:
+    same tiles, same per-tile order of operations.  Forced on at a small size (dag_min_tiles, block widths 8/4/2/1
+    all exercised through the switch points) and compared with the one-launch schedule."""
+    rng = np.random.default_rng(11)
+    n = 2560                                                   # 20 tile columns
+    M = rng.standard_normal((n, n))
+    A = M @ M.T / n + np.eye(n)
+    opts = dict(dag_min_tiles=8, nb_switch8=16, nb_switch4=10, nb_switch2=4, small_tile_threshold=40)
+    outs = {}
+    try:
+        for k, v in opts.items():
+            handle.set_option(k, v)
+        for name, extra in [('one_launch', dict(dag_streams=0)), ('chunked', dict(dag_streams=3)),
+                            ('chunked_narrow', dict(dag_streams=3, dag_min_width=2)),
+                            ('chunked_small_tiles', dict(dag_streams=5, dag_big_tiles=0)),
+                            ('no_pdl', dict(dag_streams=3, pdl=0)), ('pdl_all', dict(dag_streams=3, pdl=2))]:
+            handle.set_option('dag_streams', 4); handle.set_option('dag_min_width', 4)
+            handle.set_option('dag_big_tiles', 1); handle.set_option('pdl', 1)
+            for k, v in extra.items():
+                handle.set_option(k, v)
+            outs[name] = handle.potrf(A)
+    finally:
+        for k, v in dict(dag_min_tiles=72, nb_switch8=96, nb_switch4=64, nb_switch2=24, small_tile_threshold=2400,
+                         dag_streams=4, dag_min_width=4, dag_big_tiles=1, pdl=1).items():
+            handle.set_option(k, v)
+    ref = np.linalg.cholesky(A)
+    assert np.abs(outs['one_launch'] - ref).max() < 1e-11
+    for name in ('chunked', 'chunked_narrow', 'no_pdl', 'pdl_all'):
+        assert np.array_equal(outs[name], outs['one_launch']), name
+    # a different tile shape changes the summation order inside a tile: equal to rounding only
+    assert np.abs(outs['chunked_small_tiles'] - outs['one_launch']).max() < 1e-12
+
+
 def test_potrf_reports_not_positive_definite(handle):
     A = np.eye(300)
     A[150, 150] = -1.0

@@ -7,13 +7,12 @@ import torch
 sys.path.insert(0, '.')
 from gptest_b200 import _lib
 
-sizes = [int(a) for a in sys.argv[1:]] or [16384, 14336, 12288]
+sizes = [int(a) for a in sys.argv[1:]] or [16384, 8192, 4096]
 h = _lib.Handle(0)
 st = torch.cuda.ExternalStream(h.stream())
-VARIANTS = [dict(dag_streams=0), dict(dag_streams=4), dict(dag_streams=4, nb_switch8=96), dict(dag_streams=4, nb_switch8=80),
-            dict(dag_streams=4, nb_switch8=112), dict(dag_streams=0, nb_switch8=96), dict(dag_streams=6, nb_switch8=96),
-            dict(dag_streams=0)]
-DEFAULT = dict(dag_streams=4, stagger=1, dag_big_tiles=1, nb_switch8=0, nb_switch4=64, nb_switch2=24, dag_min_tiles=8)
+VARIANTS = [dict(), dict(dag_min_width=2), dict(dag_min_width=1), dict(dag_min_width=2, nb_switch2=16), dict(dag_min_width=2, nb_switch4=48),
+            dict(dag_min_width=2, dag_big_tiles=0), dict(dag_min_width=1, nb_switch2=32), dict()]
+DEFAULT = dict(dag_streams=4, stagger=1, dag_big_tiles=1, nb_switch8=96, dag_min_width=4, nb_switch4=64, nb_switch2=24, dag_min_tiles=8)
 out = {}
 for N in sizes:
     M = torch.randn(N, N, dtype=torch.float64, device='cuda')
