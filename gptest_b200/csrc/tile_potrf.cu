@@ -21,7 +21,13 @@
 // 256-thread barrier 15 - the chain LDS -> FMA -> rsqrt -> correction -> scale -> STS -> barrier is ~230 clocks
 // per column before any throughput term, and the kernel runs at ~745 clocks per column (50 us per tile).
 // Variants that were measured slower and dropped: two software-pipelined forms (58.7 / 69.5 us), a blocked
-// form with rank-16 updates of the later column blocks (54.5 us: fewer instructions, same chain).
+// form with rank-16 updates of the later column blocks (54.5 us: fewer instructions, same chain); a cluster of two
+// CTAs, one factoring and one building the inverse from columns pushed through distributed shared memory (75 us:
+// the factor half alone is no faster than this kernel - halving the FMAs does not shorten the chain); a ninth
+// "pivot warp" that runs the rsqrt chain of column j+1 under the update of column j (55 us: two named-barrier
+// hand-offs per column cost more than the overlap wins).  All three were bitwise identical to this kernel.
+// ncu (profiles/r01_ncu_tile_potrf.txt): 794 clocks per column, issue slots 28 % busy, FP64 pipe 22 %, stalls:
+// barrier 32 %, fixed-latency wait 19 %, shared-memory scoreboard 12 % - a latency chain, not a throughput problem.
 #include "gpb_kernels.cuh"
 
 namespace gpb {
