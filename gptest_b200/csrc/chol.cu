@@ -211,7 +211,8 @@ void chol_sweep(gpb_handle* h, FactorMat& m, const SweepPlan& plan) {
     return rem >= h->nb_switch4 ? 4 : (rem >= h->nb_switch2 ? 2 : 1);
   };
   // without a symmetric part to factor there is no panel critical path: plain order
-  const bool la = h->lookahead && factor && m.batch <= h->la_max_batch && nt > width_at(0);
+  // (up to 12 tile columns the second stream costs more than it hides: N = 1024 0.595 vs 0.622 ms)
+  const bool la = h->lookahead && factor && m.batch <= h->la_max_batch && nt > width_at(0) && (nt > 12 || m.batch > 1);
   // Programmatic dependent launch pays where the chain of small kernels IS the run time (small matrices, thin
   // sweeps: +3 % at N <= 2048, thin appends); next to a look-ahead trailing update the early-resident waiters
   // take SM slots from it (measured: -4 % at N = 8192 / 16384), so it stays off there.
