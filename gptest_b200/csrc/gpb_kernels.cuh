@@ -106,6 +106,9 @@ void launch_row_dot(const double* M, int64_t ld, int64_t m_bs, const double* x, 
 // x <- L^-1 r per batch entry by blocked forward substitution with the inverted diagonal tiles (r: scratch)
 void launch_trsv_l(const double* L, int64_t ld, int64_t l_bs, const double* Dinv, int64_t d_bs, int64_t n_pad,
                    double* r, int64_t r_bs, double* x, int64_t x_bs, int batch, cudaStream_t st, int k_begin = 0);
+// the same for m <= 16 right-hand sides stored as rows with pitch `pitch` that share one L (read once per step)
+void launch_trsv_l_multi(const double* L, int64_t ld, const double* Dinv, int64_t n_pad, double* r, double* x,
+                         int64_t pitch, int m, cudaStream_t st);
 void launch_fill(double* p, int64_t n, double v, cudaStream_t st);
 void launch_copy_sub_mean(double* dst, const double* src, int64_t n, double mean, cudaStream_t st);
 

@@ -158,6 +158,92 @@ void launch_trsv_l(const double* L, int64_t ld, int64_t l_bs, const double* Dinv
   }
 }
 
+// The same forward-substitution step for up to 16 right-hand sides that share L (rows of a thin appended block,
+// grow.cu): the 64 x 128 slice of L is read ONCE per CTA and applied to all of them.
+//   r, x: m rows with pitch `pitch` (right-hand side i at r + i * pitch); x is written, r is scratch.
+constexpr int TRSV_MULTI_MAX = 16;
+__global__ void __launch_bounds__(256) trsv_l_multi_step_kernel(const double* __restrict__ L, int64_t ld,
+                                                                   const double* __restrict__ Dinv, int k, int64_t n_pad,
+                                                                   double* __restrict__ r, double* __restrict__ x,
+                                                                   int64_t pitch, int m, int groups) {
+  __shared__ double rk[TRSV_MULTI_MAX][TILE];
+  __shared__ __align__(32) double xk[TRSV_MULTI_MAX][TILE];
+  const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
+  const int row = t & 127, h = t >> 7;
+  pdl_trigger();
+  pdl_wait();
+  for (int e = t; e < m * TILE; e += 256) rk[e >> 7][e & 127] = r[(e >> 7) * pitch + k * TILE + (e & 127)];
+  __syncthreads();
+  {
+    // x_k[i][row] = sum_c W[row][c] r_k[i][c]: thread (row, half of the columns); W is read once for all m
+    const double* W = Dinv + static_cast<int64_t>(k) * TILE * TILE + row * TILE + 64 * h;
+    double acc[TRSV_MULTI_MAX];
+#pragma unroll
+    for (int i = 0; i < TRSV_MULTI_MAX; ++i) acc[i] = 0.0;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      double w[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) w[c] = W[c0 + c];
+#pragma unroll
+      for (int i = 0; i < TRSV_MULTI_MAX; ++i) {
+        if (i < m) {
+          double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) {
+            a0 = fma(w[c], rk[i][64 * h + c0 + c], a0);
+            a1 = fma(w[c + 1], rk[i][64 * h + c0 + c + 1], a1);
+          }
+          acc[i] += a0 + a1;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < TRSV_MULTI_MAX; ++i)
+      if (i < m && h == 0) xk[i][row] = acc[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < TRSV_MULTI_MAX; ++i)
+      if (i < m && h == 1) xk[i][row] += acc[i];
+  }
+  __syncthreads();
+  if (blockIdx.x == 0)
+    for (int e = t; e < m * TILE; e += 256) x[(e >> 7) * pitch + k * TILE + (e & 127)] = xk[e >> 7][e & 127];
+  // rows below the tile: one warp per row, 4 consecutive doubles per lane; `groups` blocks of 64 rows per CTA
+  for (int gi = 0; gi < groups; ++gi) {
+    double4 lv[8];
+    int64_t rows[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {                        // eight independent row loads in flight per warp
+      rows[q] = static_cast<int64_t>(k + 1) * TILE + (static_cast<int64_t>(blockIdx.x) * groups + gi) * 64 + warp * 8 + q;
+      lv[q] = rows[q] < n_pad ? *reinterpret_cast<const double4*>(L + rows[q] * ld + static_cast<int64_t>(k) * TILE + 4 * lane)
+                              : make_double4(0.0, 0.0, 0.0, 0.0);
+    }
+    for (int i = 0; i < m; ++i) {
+      const double4 xv = *reinterpret_cast<const double4*>(&xk[i][4 * lane]);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        double s = fma(lv[q].x, xv.x, fma(lv[q].y, xv.y, fma(lv[q].z, xv.z, lv[q].w * xv.w)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && rows[q] < n_pad) r[i * pitch + rows[q]] -= s;
+      }
+    }
+  }
+}
+void launch_trsv_l_multi(const double* L, int64_t ld, const double* Dinv, int64_t n_pad, double* r, double* x,
+                         int64_t pitch, int m, cudaStream_t st) {
+  GPB_REQUIRE(m >= 1 && m <= TRSV_MULTI_MAX, "trsv_l_multi: between 1 and 16 right-hand sides");
+  const int nt = static_cast<int>(n_pad / TILE);
+  for (int k = 0; k < nt; ++k) {
+    const int64_t below = n_pad - static_cast<int64_t>(k + 1) * TILE;
+    const int groups = 1;                                // (more rows per CTA measured no faster)
+    dim3 grid(static_cast<unsigned>(below > 0 ? (below + 64 * groups - 1) / (64 * groups) : 1));
+    launch_chain(trsv_l_multi_step_kernel, grid, dim3(256), 0, st, g_pdl != 0, L, ld, Dinv, k, n_pad, r, x, pitch, m, groups);
+  }
+}
+
 __global__ void fill_kernel(double* p, int64_t n, double v) {
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)

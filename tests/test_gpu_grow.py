@@ -31,6 +31,7 @@ def natural(log_hyp):
     [100, 128, 129, 255, 256, 300],            # ending on, just after and before tile boundaries
     [1, 2, 400, 401, 1000],                    # single points and jumps over several tiles
     [640, 641, 1300],
+    [300, 301, 306, 338, 341, 383, 384, 385, 390, 512, 517, 518],   # thin appends (substitution path) and tile crossings
 ])
 def test_append_matches_full_refit(handle, cuts):
     X, y, Z, lh = data(cuts[-1], 3, seed=len(cuts) + cuts[-1])

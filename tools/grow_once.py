@@ -35,6 +35,7 @@ for rep in range(2):                                  # first pass warms up allo
         t0 = time.perf_counter()
         v = h.grow_append(X[a:a + step], y[a:a + step])
         ts.append((time.perf_counter() - t0) * 1e3)
+        out['last_append_stage_ms'] = h.timings()
     out['append_ms'] = ts
     t0 = time.perf_counter()
     fz, cov = h.grow_predict(Z)
