@@ -63,6 +63,7 @@ struct TilePotrfArgs {
 };
 void launch_tile_potrf_inv(TilePotrfArgs a, int batch, cudaStream_t st);
 void tile_potrf_init();
+void tile_potrf_set_variant(int v);
 
 // ---------------------------------------------------------------------------------------
 // SE-ARD covariance assembly

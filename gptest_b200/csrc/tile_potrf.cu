@@ -154,11 +154,157 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tile_potrf_inv_kernel(const Til
   if (t == 0 && fail < TILE) atomicCAS(p.info + batch, 0, p.k * TILE + fail + 1);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Variant 2 (the default): the owners of column j+1 run its pivot chain in the MIDDLE of step j - right after the
+// cells of their own column block have been updated and before the rest of the sweep - so that the rsqrt chain is
+// issued under the FMAs of the other seven warps instead of after them.  Same cells, same operations per cell:
+// bitwise identical to the kernel above, 46 instead of 50 us per tile (N = 1024: 0.565 vs 0.595 ms, N = 4096: 2.70 vs
+// 2.81 ms).  On top of it a split barrier (the publishing warp only arrives, triple-buffered vector, three rotating
+// barrier ids) was measured SLOWER again (0.626 ms at N = 1024) and dropped.
+// ---------------------------------------------------------------------------------------------------------
+template <int B>
+__device__ __forceinline__ void upd_col_block(double (&c)[8][8], double (&dg)[8], const double (&vr)[8], const double (&vc)[8],
+                                              const double (&vr_dg)[8], const double vr_inv, const int JB) {
+  dg[B] = fma(-vc[B], vc[B], dg[B]);
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    if (a < JB) c[a][B] = fma(-vr[a], vc[B], c[a][B]);                 // inverse rows of earlier blocks
+    else if (a == B) c[a][B] = fma(-vr_dg[a], vc[B], c[a][B]);         // diagonal 16x16 block
+    else if (a > B) c[a][B] = fma(-vr[a], vc[B], c[a][B]);             // factor rows below
+    else if (a == JB) c[a][B] = fma(-vr_inv, vc[B], c[a][B]);          // a == JB < B: inverse rows of this block
+  }
+}
+template <int BN>
+__device__ __forceinline__ void pivot_column(double (&c)[8][8], const double (&dg)[8], double* vb, int* fail, const int jn,
+                                             const int tr) {
+  const double ajj = dg[BN];
+  if (tr == 0 && !(ajj > 0.0)) atomicMin(fail, jn);
+  const double r0 = rsqrt(ajj);
+  double d = ajj * r0;
+  d = fma(0.5 * r0, fma(-d, d, ajj), d);
+  const double invd = fma(r0, fma(-d, r0, 1.0), r0);
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int r = tr + 16 * a;
+    if (r != jn) {
+      c[a][BN] *= invd;
+      vb[r] = c[a][BN];
+    } else {
+      c[a][BN] = d;
+      vb[r] = invd;
+    }
+  }
+}
+template <int JB, bool LAST>
+__device__ __forceinline__ void v2_step(double (&c)[8][8], double (&dg)[8], double (*v)[TILE], int* fail, const int jj,
+                                        const int tr, const int tc, const bool ge) {
+  const int j = 16 * JB + jj;
+  const double* vb = v[j & 1];
+  double vr[8], vc[8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a) vr[a] = vb[tr + 16 * a];
+#pragma unroll
+  for (int b = JB; b < 8; ++b) vc[b] = vb[tc + 16 * b];
+  const bool p_row = (tr <= jj);
+  vc[JB] = (tc > jj) ? vc[JB] : 0.0;
+  const double vr_inv = p_row ? vr[JB] : 0.0;
+  double vr_dg[8];
+#pragma unroll
+  for (int a = JB; a < 8; ++a) vr_dg[a] = (ge || (a == JB && p_row)) ? vr[a] : 0.0;
+  constexpr int BN = LAST ? JB + 1 : JB;                 // column block of column j+1
+  upd_col_block<JB>(c, dg, vr, vc, vr_dg, vr_inv, JB);
+  if (LAST && BN < 8) upd_col_block<(BN < 8 ? BN : 7)>(c, dg, vr, vc, vr_dg, vr_inv, JB);
+  if (BN < 8) {
+    const int tcn = LAST ? 0 : jj + 1;
+    if (tc == tcn) pivot_column<(BN < 8 ? BN : 7)>(c, dg, v[(j + 1) & 1], fail, j + 1, tr);
+  }
+#pragma unroll
+  for (int b = BN + 1; b < 8; ++b) {
+    dg[b] = fma(-vc[b], vc[b], dg[b]);
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      if (a < JB) c[a][b] = fma(-vr[a], vc[b], c[a][b]);
+      else if (a == b) c[a][b] = fma(-vr_dg[a], vc[b], c[a][b]);
+      else if (a > b) c[a][b] = fma(-vr[a], vc[b], c[a][b]);
+      else if (a == JB) c[a][b] = fma(-vr_inv, vc[b], c[a][b]);
+    }
+  }
+  __syncthreads();
+}
+template <int JB>
+__device__ __forceinline__ void v2_block(double (&c)[8][8], double (&dg)[8], double (*v)[TILE], int* fail, const int tr,
+                                         const int tc) {
+  const bool ge = (tr >= tc);
+  for (int jj = 0; jj < 15; ++jj) v2_step<JB, false>(c, dg, v, fail, jj, tr, tc, ge);
+  v2_step<JB, true>(c, dg, v, fail, 15, tr, tc, ge);
+}
+
+__global__ void __launch_bounds__(TP_THREADS, 1) tile_potrf_inv_kernel2(const TilePotrfArgs p) {
+  extern __shared__ double S[];
+  __shared__ double v[2][TILE];
+  __shared__ int fail;
+  const int t = threadIdx.x;
+  const int tc = t >> 4, tr = t & 15;
+  const int batch = blockIdx.x;
+  double* Ab = p.A + batch * p.a_batch_stride + static_cast<int64_t>(p.k) * TILE * p.lda + p.k * TILE;
+  pdl_trigger();
+  if (t == 0) fail = TILE;
+  pdl_wait();
+  double c[8][8], dg[8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int r = tr + 16 * a, cc = tc + 16 * b;
+      c[a][b] = (r >= cc) ? Ab[static_cast<int64_t>(r) * p.lda + cc] : 0.0;
+    }
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const int cc = tc + 16 * b;
+    dg[b] = Ab[static_cast<int64_t>(cc) * p.lda + cc];
+  }
+  __syncthreads();
+  if (tc == 0) pivot_column<0>(c, dg, v[0], &fail, 0, tr);
+  __syncthreads();
+  v2_block<0>(c, dg, v, &fail, tr, tc);
+  v2_block<1>(c, dg, v, &fail, tr, tc);
+  v2_block<2>(c, dg, v, &fail, tr, tc);
+  v2_block<3>(c, dg, v, &fail, tr, tc);
+  v2_block<4>(c, dg, v, &fail, tr, tc);
+  v2_block<5>(c, dg, v, &fail, tr, tc);
+  v2_block<6>(c, dg, v, &fail, tr, tc);
+  v2_block<7>(c, dg, v, &fail, tr, tc);
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) S[(tr + 16 * a) * TP_PITCH + tc + 16 * b] = c[a][b];
+  __syncthreads();
+  double* Dk = p.Dinv + batch * p.d_batch_stride + static_cast<int64_t>(p.k) * TILE * TILE;
+  for (int idx = t; idx < TILE * TILE; idx += TP_THREADS) {
+    const int r = idx >> 7, cc = idx & 127;
+    if (cc <= r) Ab[static_cast<int64_t>(r) * p.lda + cc] = S[r * TP_PITCH + cc];
+    double w = 0.0;
+    if (cc < r) w = S[cc * TP_PITCH + r];
+    else if (cc == r) w = 1.0 / S[r * TP_PITCH + r];
+    Dk[idx] = w;
+  }
+  if (t < TILE) p.diag[batch * p.diag_batch_stride + p.k * TILE + t] = S[t * TP_PITCH + t];
+  if (t == 0 && fail < TILE) atomicCAS(p.info + batch, 0, p.k * TILE + fail + 1);
+}
+
+static int g_potrf_variant = 2;       // 2: pivot inside the step (default), 0: pivot at the top of the step
+void tile_potrf_set_variant(int v) { g_potrf_variant = v; }
+
 void tile_potrf_init() {
   GPB_CUDA(cudaFuncSetAttribute(tile_potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM));
+  GPB_CUDA(cudaFuncSetAttribute(tile_potrf_inv_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM));
 }
 
 void launch_tile_potrf_inv(TilePotrfArgs a, int batch, cudaStream_t st) {
+  if (g_potrf_variant == 2) {
+    launch_chain(tile_potrf_inv_kernel2, dim3(batch), dim3(TP_THREADS), TP_SMEM, st, g_pdl != 0 && a.pdl != 0, a);
+    return;
+  }
   launch_chain(tile_potrf_inv_kernel, dim3(batch), dim3(TP_THREADS), TP_SMEM, st, g_pdl != 0 && a.pdl != 0, a);
 }
 
