@@ -179,10 +179,13 @@ __device__ __forceinline__ void pivot_column(double (&c)[8][8], const double (&d
                                              const int tr) {
   const double ajj = dg[BN];
   if (tr == 0 && !(ajj > 0.0)) atomicMin(fail, jn);
+  // 1/d and d each from the same rsqrt and ONE correction step of their own (<= 1 ulp), computed side by side:
+  // 1/d = r0 + (r0/2)(1 - a r0^2) is ready two dependent operations earlier than through d (it sits on the chain,
+  // d does not - it is only stored)
   const double r0 = rsqrt(ajj);
-  double d = ajj * r0;
-  d = fma(0.5 * r0, fma(-d, d, ajj), d);
-  const double invd = fma(r0, fma(-d, r0, 1.0), r0);
+  const double d0 = ajj * r0;
+  const double invd = fma(0.5 * r0, fma(-d0, r0, 1.0), r0);
+  const double d = fma(0.5 * r0, fma(-d0, d0, ajj), d0);
 #pragma unroll
   for (int a = 0; a < 8; ++a) {
     const int r = tr + 16 * a;
