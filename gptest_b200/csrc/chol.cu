@@ -200,9 +200,12 @@ void chol_sweep(gpb_handle* h, FactorMat& m, const SweepPlan& plan) {
   // narrow ones keep the panel short where it cannot be hidden (measured: profiles/r01_tune_potrf.json).
   // With nb_tiles == 0 the width follows the REMAINING matrix: 4 tiles while the trailing update is long
   // enough to hide a 4-tile panel, then 2, then 1 in the panel-bound tail.
+  // batches of small matrices (fewer than 24 tile columns) are throughput problems: plain order, blocks of 2 tiles
+  // (1024 x N=2048: 124.7 vs 126.1 ms, 256 x N=1024: 5.3 vs 5.6 ms; from N=4096 on the look-ahead schedule wins)
+  const bool batch_plain = m.batch > 1 && (m.batch > h->la_max_batch || nt < 24);
   auto width_at = [&](int kb) {
     if (h->nb_tiles > 0) return h->nb_tiles;
-    if (m.batch > h->la_max_batch) return 2;
+    if (batch_plain) return 2;
     // a small batch of big problems: the trailing update holds batch x the tiles, so the panel hides as it
     // would behind a single matrix sqrt(batch) times larger
     int rem = nt - kb;
@@ -212,7 +215,7 @@ void chol_sweep(gpb_handle* h, FactorMat& m, const SweepPlan& plan) {
   };
   // without a symmetric part to factor there is no panel critical path: plain order
   // (up to 12 tile columns the second stream costs more than it hides: N = 1024 0.595 vs 0.622 ms)
-  const bool la = h->lookahead && factor && m.batch <= h->la_max_batch && nt > width_at(0) && (nt > 12 || m.batch > 1);
+  const bool la = h->lookahead && factor && !batch_plain && nt > width_at(0) && nt > 12;
   // Programmatic dependent launch pays where the chain of small kernels IS the run time (small matrices, thin
   // sweeps: +3 % at N <= 2048, thin appends); next to a look-ahead trailing update the early-resident waiters
   // take SM slots from it (measured: -4 % at N = 8192 / 16384), so it stays off there.

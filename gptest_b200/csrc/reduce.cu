@@ -99,45 +99,46 @@ void launch_set_y_rows(double* A, int64_t batch_stride, int64_t row_off, const d
 __global__ void __launch_bounds__(256) trsv_l_step_kernel(const double* __restrict__ L, int64_t ld, int64_t l_bs,
                                                           const double* __restrict__ Dinv, int64_t d_bs, int k,
                                                           int64_t n_pad, double* __restrict__ r, int64_t r_bs,
-                                                          double* __restrict__ x, int64_t x_bs) {
-  __shared__ double rk[TILE];
+                                                          double* __restrict__ x, int64_t x_bs, int groups) {
+  __shared__ __align__(32) double rk[TILE];
   __shared__ __align__(32) double xk[TILE];
-  __shared__ double part[256];
   const int t = threadIdx.x, b = blockIdx.y;
   pdl_trigger();
   pdl_wait();                                    // r comes from the previous step
   double* rb = r + b * r_bs;
   if (t < TILE) rk[t] = rb[k * TILE + t];
   __syncthreads();
-  {
-    // x_k[row] = sum_{c <= row} W[row][c] r_k[c]: thread (row, half of the columns), coalescing is secondary
-    // here (128 KB tile from L2); 8 independent accumulators for memory-level parallelism
-    const int row = t & 127, h = t >> 7;
-    const double* W = Dinv + b * d_bs + static_cast<int64_t>(k) * TILE * TILE + row * TILE + 64 * h;
-    double acc[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) acc[u] = 0.0;
-#pragma unroll
-    for (int i = 0; i < 64; i += 8) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) acc[u] = fma(W[i + u], rk[64 * h + i + u], acc[u]);
-    }
-    part[t] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-  }
-  __syncthreads();
-  if (t < TILE) {
-    const double s = part[t] + part[t + 128];
-    xk[t] = s;
-    if (blockIdx.x == 0) x[b * x_bs + k * TILE + t] = s;   // not in place: other CTAs of this launch still read r_k
-  }
-  __syncthreads();
-  // rows below the tile: one warp per row, 4 consecutive doubles per lane (1 KB coalesced), fixed-order reduce
   const int warp = t >> 5, lane = t & 31;
+  {
+    // x_k[row] = sum_{c <= row} W[row][c] r_k[c]: warp w takes rows 16w..16w+15, a row is one coalesced 1 KB read
+    // (4 consecutive doubles per lane; lanes right of the diagonal skip the load: W is lower triangular), the 16
+    // row loads of a warp are independent, fixed-order butterfly reduce
+    const double* W = Dinv + b * d_bs + static_cast<int64_t>(k) * TILE * TILE;
+    const double4 rv = *reinterpret_cast<const double4*>(&rk[4 * lane]);
+    double4 wv[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int row = 16 * warp + q;
+      wv[q] = (4 * lane <= row) ? *reinterpret_cast<const double4*>(W + row * TILE + 4 * lane) : make_double4(0.0, 0.0, 0.0, 0.0);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      double s = fma(wv[q].x, rv.x, fma(wv[q].y, rv.y, fma(wv[q].z, rv.z, wv[q].w * rv.w)));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) xk[16 * warp + q] = s;
+    }
+  }
+  __syncthreads();
+  if (t < TILE && blockIdx.x == 0) x[b * x_bs + k * TILE + t] = xk[t];   // not in place: other CTAs of this launch still read r_k
+  // rows below the tile: one warp per row, 4 consecutive doubles per lane (1 KB coalesced), fixed-order reduce
   const double4 xv = *reinterpret_cast<const double4*>(&xk[4 * lane]);
   const double* Lb = L + b * l_bs;
+  // a CTA takes `groups` blocks of 64 rows: every CTA reads the 128 KB W tile first, so few long CTAs beat many short
+  for (int gi = 0; gi < groups; ++gi)
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const int64_t row = static_cast<int64_t>(k + 1) * TILE + static_cast<int64_t>(blockIdx.x) * 64 + warp * 8 + q;
+    const int64_t row = static_cast<int64_t>(k + 1) * TILE + (static_cast<int64_t>(blockIdx.x) * groups + gi) * 64 + warp * 8 + q;
     if (row < n_pad) {
       const double4 lv = *reinterpret_cast<const double4*>(Lb + row * ld + static_cast<int64_t>(k) * TILE + 4 * lane);
       double s = fma(lv.x, xv.x, fma(lv.y, xv.y, fma(lv.z, xv.z, lv.w * xv.w)));
@@ -153,8 +154,11 @@ void launch_trsv_l(const double* L, int64_t ld, int64_t l_bs, const double* Dinv
   const int nt = static_cast<int>(n_pad / TILE);
   for (int k = k_begin; k < nt; ++k) {
     const int64_t below = n_pad - static_cast<int64_t>(k + 1) * TILE;
-    dim3 grid(static_cast<unsigned>(below > 0 ? (below + 63) / 64 : 1), batch);
-    launch_chain(trsv_l_step_kernel, grid, dim3(256), 0, st, g_pdl != 0, L, ld, l_bs, Dinv, d_bs, k, n_pad, r, r_bs, x, x_bs);
+    // batched sweeps have CTAs to spare: four row blocks per CTA quarter the re-reads of W
+    const int groups = (batch >= 64 && below >= 512) ? 8 : ((batch >= 16 && below >= 256) ? 4 : 1);
+    dim3 grid(static_cast<unsigned>(below > 0 ? (below + 64 * groups - 1) / (64 * groups) : 1), batch);
+    launch_chain(trsv_l_step_kernel, grid, dim3(256), 0, st, g_pdl != 0, L, ld, l_bs, Dinv, d_bs, k, n_pad, r, r_bs, x, x_bs,
+                 groups);
   }
 }
 

@@ -249,7 +249,8 @@ def test_batched_nlml_equals_single_calls(handle):
         vals2, _ = handle.gpr_nlml_batched(kh)
     finally:
         handle.set_option('batch_chunk', 0)
-    assert np.array_equal(vals, vals2)
+    # (a chunk of one problem takes the single-matrix schedule, i.e. other block widths: equal to rounding)
+    assert rel(vals, vals2) < 1e-13
 
 
 # ---------------------------------------------------------------------------------------
