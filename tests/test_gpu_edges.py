@@ -173,3 +173,29 @@ def test_matern_dropin_names_and_growing_set(handle):
     fz, cov = handle.grow_predict(Z)
     rf, rc = gpr_oracle.predict_kind(lh, X, y, Z, 'Matern32')
     assert np.abs(fz - rf).max() < 1e-9 and np.abs(cov - rc).max() < 1e-9
+
+
+def test_two_handles_are_independent(handle):
+    """Different handles own their work space and streams: interleaved calls must not disturb each other
+    (include/gpb200.h: 'different handles are independent')."""
+    from gptest_b200 import _lib
+    other = _lib.Handle(0)
+    try:
+        rng = np.random.default_rng(21)
+        Xa, Xb = rng.random((500, 3)), rng.random((333, 2))
+        ya, yb = np.sin(Xa.sum(1)), np.cos(Xb.sum(1))
+        lha, lhb = np.log([0.6] * 3 + [1.0, 0.1]), np.log([0.4] * 2 + [1.2, 0.2])
+        handle.set_train(Xa, ya)
+        other.set_train(Xb, yb)
+        other.grow_begin(natural(lhb), 2, capacity=400)
+        other.grow_append(Xb[:200], yb[:200])
+        va = handle.gpr_nlml(natural(lha))
+        vb = other.gpr_nlml(natural(lhb), kind=1)              # Matern on one handle ...
+        va2, ga = handle.gpr_nlml(natural(lha), want_grad=True)  # ... squared exponential on the other
+        vg = other.grow_append(Xb[200:], yb[200:])
+        assert abs(va - gpr_oracle.nlml_chol(lha, Xa, ya)) <= 1e-8 * abs(va) and abs(va2 - va) <= 1e-12 * abs(va)
+        assert abs(vb - gpr_oracle.nlml_kind(lhb, Xb, yb, 'Matern32')) <= 1e-8 * abs(vb)
+        assert abs(vg - gpr_oracle.nlml_chol(lhb, Xb, yb)) <= 1e-8 * abs(vg)
+        assert np.abs(ga - gpr_oracle.nlml_grad(lha, Xa, ya)).max() <= 1e-7 * max(1.0, np.abs(ga).max())
+    finally:
+        other.close()
