@@ -235,6 +235,8 @@ int gpb_set_option(gpb_handle* h, const char* name, int64_t value) {
   else if (!strcmp(name, "dag_streams")) h->dag_streams = static_cast<int>(value < 0 ? 0 : (value > 16 ? 16 : value));
   else if (!strcmp(name, "dag_min_tiles")) h->dag_min_tiles = static_cast<int>(value);
   else if (!strcmp(name, "dag_big_tiles")) h->dag_big_tiles = static_cast<int>(value);
+  else if (!strcmp(name, "chain_on_panel_stream")) h->chain_on_panel_stream = static_cast<int>(value);
+  else if (!strcmp(name, "pdl_max_tiles")) h->pdl_max_tiles = static_cast<int>(value);
   else if (!strcmp(name, "dag_min_width")) h->dag_min_width = static_cast<int>(value < 1 ? 1 : value);
   else if (!strcmp(name, "nb_switch4")) h->nb_switch4 = static_cast<int>(value);
   else if (!strcmp(name, "nb_switch2")) h->nb_switch2 = static_cast<int>(value);

@@ -219,7 +219,7 @@ void chol_sweep(gpb_handle* h, FactorMat& m, const SweepPlan& plan) {
   // Programmatic dependent launch pays where the chain of small kernels IS the run time (small matrices, thin
   // sweeps: +3 % at N <= 2048, thin appends); next to a look-ahead trailing update the early-resident waiters
   // take SM slots from it (measured: -4 % at N = 8192 / 16384), so it stays off there.
-  s.pdl = !la || nt <= 24;
+  s.pdl = !la || nt <= h->pdl_max_tiles;
 
   if (!la) {
     for (int kb = 0; kb < nt;) {
@@ -286,6 +286,30 @@ void chol_sweep(gpb_handle* h, FactorMat& m, const SweepPlan& plan) {
       GPB_CUDA(cudaEventRecord(e, h->su[i]));
       GPB_CUDA(cudaStreamWaitEvent(h->s0, e, 0));
     }
+  }
+  // The panel stream carries the whole critical chain - update of the next panel's columns, diagonal tile, TRSM -
+  // as consecutive launches of ONE stream (no event hop inside the chain, programmatic dependent launch applies);
+  // the main stream only applies each finished panel to the columns further right.  Per step two events: `er`
+  // (main -> panel: the previous rest-update has reached the next panel's columns) and `ep` (panel -> main).
+  if (h->chain_on_panel_stream) {
+    cudaEvent_t er = h->next_event();
+    GPB_CUDA(cudaEventRecord(er, h->s0));              // panel [kb, kend) and everything before it
+    while (kend < nt) {
+      const int nbn = width_at(kend);
+      const int nend = kend + nbn < nt ? kend + nbn : nt;
+      GPB_CUDA(cudaStreamWaitEvent(h->s1, er, 0));
+      s.update(kend, nend, kb, kend, h->s1);           // columns of the next panel ...
+      s.panel(kend, nend, h->s1);                      // ... and the panel itself, back to back
+      cudaEvent_t ep = h->next_event();
+      GPB_CUDA(cudaEventRecord(ep, h->s1));
+      s.update(nend, nt, kb, kend, h->s0);             // meanwhile the rest of the update
+      er = h->next_event();
+      GPB_CUDA(cudaEventRecord(er, h->s0));
+      GPB_CUDA(cudaStreamWaitEvent(h->s0, ep, 0));
+      kb = kend;
+      kend = nend;
+    }
+    return;
   }
   while (kend < nt) {
     const int nbn = width_at(kend);

@@ -64,6 +64,8 @@ struct gpb_handle {
   int64_t batch_chunk = 0;       // 0 = auto
   int dag_streams = 4;           // > 0: while the block is 4 tiles wide, the trailing update is issued as column chunks
                                  // on this many streams, ordered by events only (see chol.cu); 0 = one launch per step
+  int pdl_max_tiles = 40;        // look-ahead sweeps of larger matrices launch without programmatic serialisation
+  int chain_on_panel_stream = 1; // the update of the next panel's columns runs on the panel stream (chol.cu)
   int dag_min_width = 4;         // narrowest block (tiles) that still uses the chunked schedule
   int dag_big_tiles = 1;         // chunk updates keep the 128-row tiles although each launch is small
   int dag_min_tiles = 72;        // matrices with fewer tile columns keep the one-launch schedule
