@@ -46,9 +46,13 @@ const char* gpb_last_error(gpb_handle* h);            /* h may be NULL: last cre
  * "cov_kind" (covariance of the regression entry points: 0 squared exponential = GPr.py:90-110, the default;
  * 1 Matern 3/2, 2 Matern 5/2 - same hyper-parameter layout and ARD scaling; extension),
  * "batch_chunk" (problems resident at once in the batched path), "la_max_batch" (largest batch that
- * uses the look-ahead schedule; default: all), and the schedule knobs "nb_switch4", "nb_switch2",
- * "split_tiles", "small_tile_threshold", "persistent_waves", "stagger" (see gpb_context.cuh).
- * Returns <0 if unknown. */
+ * uses the look-ahead schedule; default: all), and the schedule knobs (defaults are the measured best; the A/B
+ * scripts under tools/ use them): "nb_switch8", "nb_switch4", "nb_switch2" (block width 8/4/2 tiles while at least
+ * that many tile columns remain), "split_tiles", "small_tile_threshold", "dag_streams", "dag_min_tiles",
+ * "dag_min_width", "dag_big_tiles" (chunked multi-stream trailing update), "chain_on_panel_stream", "pdl",
+ * "pdl_max_tiles" (programmatic dependent launch), "potrf_variant", "persistent_waves", "stagger"
+ * (see gpb_context.cuh).  "pdl", "potrf_variant", "persistent_waves" and "stagger" are process-wide, the rest per
+ * handle.  Returns <0 if unknown. */
 int gpb_set_option(gpb_handle* h, const char* name, int64_t value);
 /* stage times (ms) of the last GPr/potrf call measured with CUDA events on the handle's
  * stream: [0]=covariance assembly [1]=factorisation (+fused forward solves)
