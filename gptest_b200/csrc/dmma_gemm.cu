@@ -267,6 +267,8 @@ static int g_persistent_waves = 0;
 void dmma_gemm_set_persistent(int waves) { g_persistent_waves = waves < 0 ? 0 : waves; }
 int g_pdl = 1;
 void dmma_gemm_set_pdl(int mode) { g_pdl = mode < 0 ? 0 : mode; }
+static int g_fine_warps = 1;
+void dmma_gemm_set_fine_warps(int on) { g_fine_warps = on != 0; }
 static int g_stagger = 1;
 void dmma_gemm_set_stagger(int on) { g_stagger = on != 0; }
 
@@ -274,6 +276,10 @@ void dmma_gemm_init() {
   GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<128, 128, 2, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 smem_bytes(128, 128)));
   GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<64, 64, 2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                smem_bytes(64, 64)));
+  GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<64, 128, 2, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                smem_bytes(64, 128)));
+  GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<64, 64, 2, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 smem_bytes(64, 64)));
   GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<64, 128, 2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 smem_bytes(64, 128)));
@@ -325,12 +331,23 @@ void launch_dmma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmArgs
     launch_chain(dmma_gemm_nt_kernel<128, 64, 2, 2, 2>, grid_for(2 * ntiles, 2), dim3(4 * 32), smem_bytes(128, 64), st, pdl,
                  mapA, mapB, a);
   } else if (tile == 64) {
-    launch_chain(dmma_gemm_nt_kernel<64, 64, 2, 2, 3>, grid_for(ntiles, 3), dim3(4 * 32), smem_bytes(64, 64), st, pdl,
-                 mapA, mapB, a);
+    // A launch that leaves SMs with a single CTA is latency bound (one warp per scheduler: 1.34 us per 16-deep k
+    // step for a lone 4-warp CTA, 40 % of the pipe rate): such launches - the panel's critical chain - use 8 warps
+    // with half-size warp tiles, two warps per scheduler covering each other's fragment loads.
+    if (g_fine_warps && static_cast<int64_t>(ntiles) * a.nbatch <= g_num_sms)
+      launch_chain(dmma_gemm_nt_kernel<64, 64, 2, 4, 3>, grid_for(ntiles, 3), dim3(8 * 32), smem_bytes(64, 64), st, pdl,
+                   mapA, mapB, a);
+    else
+      launch_chain(dmma_gemm_nt_kernel<64, 64, 2, 2, 3>, grid_for(ntiles, 3), dim3(4 * 32), smem_bytes(64, 64), st, pdl,
+                   mapA, mapB, a);
   } else {
     // 64 x 128: rows in units of 64, columns in units of 128 (mapA with 64-row boxes, mapB with 128-row boxes)
-    launch_chain(dmma_gemm_nt_kernel<64, 128, 2, 2, 2>, grid_for(ntiles, 2), dim3(4 * 32), smem_bytes(64, 128), st, pdl,
-                 mapA, mapB, a);
+    if (g_fine_warps && static_cast<int64_t>(ntiles) * a.nbatch <= g_num_sms)
+      launch_chain(dmma_gemm_nt_kernel<64, 128, 2, 4, 2>, grid_for(ntiles, 2), dim3(8 * 32), smem_bytes(64, 128), st, pdl,
+                   mapA, mapB, a);
+    else
+      launch_chain(dmma_gemm_nt_kernel<64, 128, 2, 2, 2>, grid_for(ntiles, 2), dim3(4 * 32), smem_bytes(64, 128), st, pdl,
+                   mapA, mapB, a);
   }
 }
 
