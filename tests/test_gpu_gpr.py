@@ -121,6 +121,39 @@ def test_chunked_schedule_and_dependent_launch_are_bitwise_equivalent(handle):
     assert np.abs(outs['chunked_small_tiles'] - outs['one_launch']).max() < 1e-12
 
 
+def test_full_size_schedule_is_race_free(handle):
+    """The default schedule at a size where all of it is active (chunked multi-stream updates with 8- and 4-tile
+    blocks, look-ahead tail, chain on the panel stream): repeated runs must give the same bits as each other and as
+    the plain one-launch-per-step order (no look-ahead, no chunks) with the same block widths."""
+    import torch
+    n = 14336                                                  # 112 tile columns: 8-tile, 4-tile, 2-tile and 1-tile phases
+    g = torch.Generator(device='cuda').manual_seed(5)
+    M = torch.randn(n, 512, dtype=torch.float64, device='cuda', generator=g)
+    K = M @ M.T / 512 + torch.eye(n, dtype=torch.float64, device='cuda')
+    del M
+    W = torch.empty_like(K)
+    outs = []
+    try:
+        for rep in range(3):
+            W.copy_(K)
+            torch.cuda.synchronize()
+            assert handle.potrf_dev(W.data_ptr(), n, n) == 0
+            outs.append(torch.tril(W).clone())
+        handle.set_option('lookahead', 0)
+        W.copy_(K)
+        torch.cuda.synchronize()
+        assert handle.potrf_dev(W.data_ptr(), n, n) == 0
+        plain = torch.tril(W).clone()
+    finally:
+        handle.set_option('lookahead', 1)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert torch.equal(outs[0], plain)
+    # and it is a factor of K (probe columns)
+    cols = torch.tensor([0, 1, 127, 128, 4097, n - 129, n - 1], device='cuda')
+    R = outs[0] @ outs[0][cols].T - K[:, cols]
+    assert float(R.abs().max()) < 1e-11 * float(K.abs().max())
+
+
 def test_potrf_reports_not_positive_definite(handle):
     A = np.eye(300)
     A[150, 150] = -1.0
