@@ -84,14 +84,9 @@ class PrefProbit(object):
         return W, g.reshape(-1, 1)
 
     def log_marginal(self, uvi, y, f, iK, logdetK):
-        """GPpref.py:90-94 for caller-supplied iK / logdetK (small host expression; inside
-        ``calc_laplace`` the same quantity is reduced on the device)."""
-        from math import erfc, log, sqrt
-        z = np.asarray(self.z_k(uvi, f, y), dtype=float).reshape(-1)
-        s = sum(log(0.5 * erfc(-zi / sqrt(2.0))) for zi in z)
-        fv = np.asarray(f, dtype=float).reshape(-1, 1)
-        psi = s - 0.5 * (fv.T @ iK @ fv) - 0.5 * logdetK - iK.shape[0] / 2.0 * self.log2pi
-        return np.asarray(psi).flat[0]
+        """GPpref.py:90-94 for caller-supplied iK / logdetK, reduced on the device (the same kernel that
+        ``calc_laplace`` uses per iteration); returns a python float like the reference's ``psi.flat[0]``."""
+        return _handle().pref_log_marginal(uvi, y, f, iK, float(np.asarray(logdetK).reshape(-1)[0]), sigma=self.sigma)
 
 
 class PreferenceGaussianProcess(object):

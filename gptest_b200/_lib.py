@@ -55,6 +55,7 @@ SIGNATURES = {
     'gpb_gpc_predict': (C.c_int, [C.c_void_p, c_dp, C.c_int64, c_dp, c_dp, c_dp]),
     'gpb_pref_laplace': (C.c_int, [C.c_void_p, c_lp, c_dp, C.c_int64, c_dp, C.c_double, C.c_double, C.c_int32,
                                    C.c_int32, C.c_int32, c_dp, c_dp, c_ip, c_dp, c_dp, c_ip]),
+    'gpb_pref_log_marginal': (C.c_int, [C.c_void_p, c_lp, c_dp, C.c_int64, C.c_int64, c_dp, c_dp, C.c_double, C.c_double, c_dp]),
     'gpb_pref_evidence': (C.c_int, [C.c_void_p, c_dp]),
     'gpb_pref_predict': (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int64, c_dp, c_dp, c_dp]),
     'gpb_pref_derivatives': (C.c_int, [C.c_void_p, c_lp, c_dp, C.c_int64, C.c_int64, c_dp, C.c_double,
@@ -398,6 +399,19 @@ def _pref_predict(self, Z, Zb=None):
     return mean, var, prob
 
 
+def _pref_log_marginal(self, uvi, y, f, iK, logdetK, sigma=1.0):
+    uvi = np.ascontiguousarray(uvi, dtype=np.int64).reshape(-1, 2)
+    y = as_f64(y).reshape(-1)
+    f = as_f64(f).reshape(-1)
+    iK = as_f64(iK)
+    assert iK.shape == (len(f), len(f)) and len(y) == len(uvi)
+    v = np.empty(1)
+    self.check(self.lib.gpb_pref_log_marginal(self.h, uvi.ctypes.data_as(c_lp), _dp(y), len(uvi), len(f), _dp(f), _dp(iK),
+                                              float(logdetK), float(sigma), _dp(v)))
+    return float(v[0])
+
+
+Handle.pref_log_marginal = _pref_log_marginal
 Handle.pref_evidence = _pref_evidence
 Handle.pref_predict = _pref_predict
 Handle.pref_laplace = _pref_laplace

@@ -648,6 +648,44 @@ int gpb_pref_derivatives(gpb_handle* h, const int64_t* uvi, const double* y, int
   LAP_END
 }
 
+int gpb_pref_log_marginal(gpb_handle* h, const int64_t* uvi, const double* y, int64_t P, int64_t n, const double* f,
+                          const double* iK, double logdetK, double sigma, double* out) {
+  LAP_BEGIN
+  GPB_REQUIRE(uvi && y && f && iK && out && P > 0 && n > 0, "null argument");
+  for (int64_t k = 0; k < 2 * P; ++k) GPB_REQUIRE(uvi[k] >= 0 && uvi[k] < n, "uvi index out of range");
+  const int64_t ne = round_up(n, 2);                       // even pitch for the 16-byte loads of row_dot
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+  const size_t o_uvi = take(P * 16), o_y = take(P * 8), o_f = take(ne * 8), o_f2 = take(ne * 8), o_t = take(ne * 8),
+               o_sc = take(64);
+  h->aux1.ensure(off);
+  h->aux2.ensure(static_cast<size_t>(n) * ne * 8);
+  char* base = h->aux1.as<char>();
+  double* fd = reinterpret_cast<double*>(base + o_f);
+  double* f2 = reinterpret_cast<double*>(base + o_f2);
+  double* td = reinterpret_cast<double*>(base + o_t);
+  double* sc = reinterpret_cast<double*>(base + o_sc);
+  GPB_CUDA(cudaMemsetAsync(base, 0, off, h->s0));
+  GPB_CUDA(cudaMemsetAsync(h->aux2.p, 0, static_cast<size_t>(n) * ne * 8, h->s0));
+  GPB_CUDA(cudaMemcpyAsync(base + o_uvi, uvi, P * 16, cudaMemcpyHostToDevice, h->s0));
+  GPB_CUDA(cudaMemcpyAsync(base + o_y, y, P * 8, cudaMemcpyHostToDevice, h->s0));
+  GPB_CUDA(cudaMemcpyAsync(fd, f, n * 8, cudaMemcpyHostToDevice, h->s0));
+  GPB_CUDA(cudaMemcpyAsync(f2, f, n * 8, cudaMemcpyHostToDevice, h->s0));
+  GPB_CUDA(cudaMemcpy2DAsync(h->aux2.p, ne * 8, iK, n * 8, n * 8, n, cudaMemcpyHostToDevice, h->s0));
+  GPB_CUDA(cudaMemcpyAsync(sc, &logdetK, 8, cudaMemcpyHostToDevice, h->s0));
+  launch_row_dot(h->aux2.as<double>(), ne, 0, fd, 0, n, ne, 0, td, 0, 1, h->s0);            // t = iK f
+  const double isq = 1.0 / (sigma * std::sqrt(2.0));
+  pref_finish_kernel<<<1, 1024, 0, h->s0>>>(reinterpret_cast<const int64_t*>(base + o_uvi),
+                                            reinterpret_cast<const double*>(base + o_y), P, n, isq, fd, f2, td, sc, sc + 2);
+  GPB_CUDA(cudaGetLastError());
+  h->launches += 2;
+  double* host = h->pinned(64);
+  GPB_CUDA(cudaMemcpyAsync(host, sc + 2, 16, cudaMemcpyDeviceToHost, h->s0));
+  GPB_CUDA(cudaStreamSynchronize(h->s0));
+  *out = host[1];
+  LAP_END
+}
+
 int gpb_pref_laplace(gpb_handle* h, const int64_t* uvi, const double* y, int64_t P, const double* khyp, double sigma,
                      double delta_f, int32_t max_iter, int32_t grad_mode, int32_t use_f0, double* f_inout, double* lml,
                      int32_t* iters, double* trace, double* jitter, int32_t* info) {

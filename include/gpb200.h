@@ -163,6 +163,10 @@ int gpb_pref_laplace(gpb_handle* h, const int64_t* uvi, const double* y, int64_t
 int gpb_pref_evidence(gpb_handle* h, double* evidence);
 int gpb_pref_predict(gpb_handle* h, const double* Z, const double* Zb, int64_t mz, double* mean, double* var,
                      double* prob);
+/* PrefProbit.log_marginal (GPpref.py:90-94) for caller-supplied f (n), iK (n x n, host) and logdetK:
+ * sum log Phi(z) - f' iK f / 2 - logdetK / 2 - n/2 log(2 pi), reduced on the device. */
+int gpb_pref_log_marginal(gpb_handle* h, const int64_t* uvi, const double* y, int64_t P, int64_t n, const double* f,
+                          const double* iK, double logdetK, double sigma, double* out);
 /* PrefProbit.derivatives (GPpref.py:68-88) on its own: dense W (n x n) and gradient (n). */
 int gpb_pref_derivatives(gpb_handle* h, const int64_t* uvi, const double* y, int64_t P, int64_t n,
                          const double* f, double sigma, int32_t grad_mode, double* W_out, double* g_out);

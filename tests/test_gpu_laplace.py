@@ -220,3 +220,21 @@ def test_gppref_dropin_extensions(handle):
     assert abs(ev - ref) <= 1e-8 * max(1.0, abs(ref))
     mu, var, p = gp.predict_preference(x[:5], x[5:10])
     assert p.shape == (5,) and np.all(var > -1e-9)
+
+
+@pytest.mark.parametrize("n,P", [(40, 120), (77, 300)])
+def test_pref_log_marginal_on_device(handle, n, P):
+    """PrefProbit.log_marginal (GPpref.py:90-94) with caller-supplied iK / logdetK, odd and even n."""
+    from gptest_b200 import GPpref
+    x, uvi, y = make_pref(n, P, 3, seed=n)
+    rng = np.random.default_rng(n)
+    f = 0.3 * rng.standard_normal((n, 1))
+    K = gppref_oracle.rbf_ard_K(x, np.array([0.5, 0.5, 0.5]), 1.3) + 1e-6 * np.eye(n)
+    L = np.linalg.cholesky(K)
+    iK = np.linalg.inv(K)
+    logdetK = np.sum(np.log(np.diag(L)))                       # GPpref.py:131
+    for sigma in (1.0, 0.4):
+        ref = gppref_oracle.ProbitPrefOracle(sigma).log_marginal(uvi, y, f, iK, logdetK)
+        lik = GPpref.PrefProbit(sigma)
+        got = lik.log_marginal(uvi, y, f, iK, logdetK)
+        assert isinstance(got, float) and abs(got - ref) <= 1e-10 * max(1.0, abs(ref))
