@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tile_potrf_inv_kernel(const Til
 // issued under the FMAs of the other seven warps instead of after them.  Same cells, same operations per cell:
 // bitwise identical to the kernel above, 46 instead of 50 us per tile (N = 1024: 0.565 vs 0.595 ms, N = 4096: 2.70 vs
 // 2.81 ms).  On top of it a split barrier (the publishing warp only arrives, triple-buffered vector, three rotating
-// barrier ids) was measured SLOWER again (0.626 ms at N = 1024) and dropped.
+// barrier ids) was measured SLOWER again (0.626 ms at N = 1024) and dropped.  A probe that skips the publishing warp's
+// remaining sweep altogether (wrong results, timing only) gains just 4 us per tile: deferring that work would not pay.
 // ---------------------------------------------------------------------------------------------------------
 template <int B>
 __device__ __forceinline__ void upd_col_block(double (&c)[8][8], double (&dg)[8], const double (&vr)[8], const double (&vc)[8],
