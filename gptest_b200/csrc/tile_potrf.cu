@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tile_potrf_inv_kernel(const Til
 // 2.81 ms).  On top of it a split barrier (the publishing warp only arrives, triple-buffered vector, three rotating
 // barrier ids) was measured SLOWER again (0.626 ms at N = 1024) and dropped.  A probe that skips the publishing warp's
 // remaining sweep altogether (wrong results, timing only) gains just 4 us per tile: deferring that work would not pay.
+// With 512 threads (the 8 row groups of a thread split over two thread halves, four warps per scheduler) the tile takes
+// 52 us: bitwise identical again, slower again (costlier barrier, the pivot computed twice, 128-register cap).
 // ---------------------------------------------------------------------------------------------------------
 template <int B>
 __device__ __forceinline__ void upd_col_block(double (&c)[8][8], double (&dg)[8], const double (&vr)[8], const double (&vc)[8],
