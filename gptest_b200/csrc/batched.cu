@@ -30,7 +30,7 @@ extern "C" int gpb_gpr_nlml_batched(gpb_handle* h, const double* khyp, int64_t B
     // problems resident at once: bounded by memory (A + Dinv per problem) and by option
     const size_t per_problem = static_cast<size_t>(np) * np * 8 + static_cast<size_t>(np) * TILE * 8 +
                                static_cast<size_t>(d + 2) * np * 8;
-    int64_t chunk = h->batch_chunk > 0 ? h->batch_chunk : 256;
+    int64_t chunk = h->batch_chunk > 0 ? h->batch_chunk : 296;     // two full waves of the one-CTA-per-tile panel kernel on 148 SMs
     if (chunk > B) chunk = B;
     if (chunk > 65535) chunk = 65535;
     if (static_cast<size_t>(chunk) * np * np * 8 > h->A.bytes) {
