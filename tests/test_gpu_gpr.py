@@ -110,7 +110,7 @@ def test_chunked_schedule_and_dependent_launch_are_bitwise_equivalent(handle):
                 handle.set_option(k, v)
             outs[name] = handle.potrf(A)
     finally:
-        for k, v in dict(dag_min_tiles=72, nb_switch8=96, nb_switch4=64, nb_switch2=32, small_tile_threshold=2400,
+        for k, v in dict(dag_min_tiles=72, nb_switch8=96, nb_switch4=64, nb_switch2=40, small_tile_threshold=2400,
                          dag_streams=4, dag_min_width=4, dag_big_tiles=1, pdl=1).items():
             handle.set_option(k, v)
     ref = np.linalg.cholesky(A)

@@ -12,7 +12,7 @@ h = _lib.Handle(0)
 st = torch.cuda.ExternalStream(h.stream())
 VARIANTS = [dict(), dict(dag_min_width=2), dict(dag_min_width=1), dict(dag_min_width=2, nb_switch2=16), dict(dag_min_width=2, nb_switch4=48),
             dict(dag_min_width=2, dag_big_tiles=0), dict(dag_min_width=1, nb_switch2=32), dict()]
-DEFAULT = dict(dag_streams=4, stagger=1, dag_big_tiles=1, nb_switch8=96, dag_min_width=4, nb_switch4=64, nb_switch2=32, dag_min_tiles=8)
+DEFAULT = dict(dag_streams=4, stagger=1, dag_big_tiles=1, nb_switch8=96, dag_min_width=4, nb_switch4=64, nb_switch2=40, dag_min_tiles=8)
 out = {}
 for N in sizes:
     M = torch.randn(N, N, dtype=torch.float64, device='cuda')
