@@ -24,6 +24,7 @@ import types
 import numpy as np
 
 REF = '/root/reference'
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # also runnable as a plain script
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
 
 
