@@ -164,6 +164,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tile_potrf_inv_kernel(const Til
 // remaining sweep altogether (wrong results, timing only) gains just 4 us per tile: deferring that work would not pay.
 // With 512 threads (the 8 row groups of a thread split over two thread halves, four warps per scheduler) the tile takes
 // 52 us: bitwise identical again, slower again (costlier barrier, the pivot computed twice, 128-register cap).
+// A probe that drops every second barrier (wrong results, timing only) gains 4.5 us per tile: that bounds what a
+// two-columns-per-barrier formulation (pair panels factored inside one warp, rank-2 sweeps) could win.
 // ---------------------------------------------------------------------------------------------------------
 template <int B>
 __device__ __forceinline__ void upd_col_block(double (&c)[8][8], double (&dg)[8], const double (&vr)[8], const double (&vc)[8],
