@@ -32,47 +32,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_FIT, D_FIT, M_TEST = 16384, 8, 1024
+from bench_configs import N_FIT, D_FIT, M_TEST, make_c2, make_c3, make_c4, make_c5, khyp_of  # noqa: E402
+
 METRIC = "GP fits/sec at N=16384 fp64 (kernel+Cholesky+solve+LML)"
 WORKLOAD = "GPr N=16384 D=8 SE-ARD fp64 compute_likelihood (BASELINE configs[1])"
-
-
-def make_c2(n=N_FIT, d=D_FIT):
-    """SURVEY 8(d) C2 recipe."""
-    rng = np.random.default_rng(0)
-    X = rng.random((n, d))
-    w = rng.standard_normal(d)
-    y = np.sin(X @ w) + 0.1 * rng.standard_normal(n)
-    Z = rng.random((M_TEST, d))
-    log_hyp = np.log([0.5] * d + [1.0, 0.1])
-    return X, y, Z, log_hyp
-
-
-def make_c5(n=2048, B=1024):
-    """SURVEY 8(d) C5 recipe: GP_parameter_fit.py:9-28 data, 32x32 hyper-parameter grid."""
-    rng = np.random.default_rng(0)
-    X = 100 * rng.random((n, 2))
-    a, b = X[:, 0], X[:, 1]
-    cost = 3.0 + 10 * np.exp(-np.sqrt((a - 40) ** 2 + (b - 40) ** 2) / 16) \
-        + 7 * np.exp(-np.sqrt((a - 10) ** 2 + (b - 90) ** 2) / 12) \
-        + 4 * np.exp(-np.sqrt((a - 80) ** 2 + (b - 60) ** 2) / 32) \
-        + 7 * np.exp(-np.sqrt((a + 20) ** 2 + (b - 50) ** 2) / 32) \
-        + 7 * np.exp(-np.sqrt((a - 120) ** 2 + (b - 50) ** 2) / 32) \
-        + 12 * np.exp(-np.sqrt((a - 80) ** 2 + (b - 20) ** 2) / 8) \
-        + 5 * np.exp(-np.sqrt((a - 60) ** 2 + (b - 80) ** 2) / 10) \
-        + 3 * np.exp(-np.sqrt((a - 90) ** 2 + (b - 90) ** 2) / 20)
-    Y = cost + 0.25 * rng.standard_normal(n) - 3.0
-    g = int(round(np.sqrt(B)))
-    ll = np.linspace(np.log(2), np.log(200), g)
-    lf = np.linspace(np.log(0.3), np.log(30), g)
-    L, F = np.meshgrid(ll, lf, indexing='ij')
-    lh = np.stack([L.ravel(), L.ravel(), F.ravel(), np.full(g * g, np.log(0.25))], axis=1)[:B]
-    return X, Y, lh
-
-
-def khyp_of(log_hyp):
-    h = np.exp(np.asarray(log_hyp, dtype=float))
-    return np.concatenate([h[:-2], [h[-2] ** 2, h[-1] ** 2]])
 
 
 # ------------------------------------------------------------------------------------------
@@ -419,34 +382,23 @@ def single_gpu_extras(h, X, y, Z, lh):
 
 
 def other_configs(h):
-    """BASELINE configs 3 and 4 at full size, device time of one call each (recipes: SURVEY 8d)."""
-    from math import erfc, sqrt
+    """BASELINE configs 3 and 4 at full size, device time of one call each (recipes: bench_configs.py)."""
     res = {}
-    rng = np.random.default_rng(0)
-    ndtr = np.vectorize(lambda v: 0.5 * erfc(-v / sqrt(2.0)))
-    n, D = 8192, 4
-    Xc = rng.random((n, D))
-    w = rng.standard_normal(D)
-    lat = np.sin(2 * np.pi * Xc @ w / np.abs(w).sum() + np.pi / 4) + 0.2
-    yc = np.where(rng.random(n) < ndtr(lat), 1.0, -1.0)
+    Xc, yc, _, lhc = make_c3()
+    D = Xc.shape[1]
     h.set_train(Xc)
     for _ in range(2):
         t0 = time.perf_counter()
-        f, lml, iters, trace, jit = h.gpc_laplace(yc, np.r_[[0.5] * D, 1.0], link=0, delta_f=1e-6)
+        f, lml, iters, trace, jit = h.gpc_laplace(yc, np.r_[np.exp(lhc[:D]), np.exp(lhc[D]) ** 2], link=0, delta_f=1e-6)
         dt = (time.perf_counter() - t0) * 1e3
     res["c3_gpc_n8192_d4"] = {"ms": dt, "newton_iters": int(iters), "lml": lml}
-    n, D, P = 4096, 6, 32768
-    Xp = rng.random((n, D))
-    uvi = rng.integers(0, n, (P, 2))
-    bad = uvi[:, 0] == uvi[:, 1]
-    uvi[bad, 1] = (uvi[bad, 0] + 1) % n
-    w = rng.standard_normal(D)
-    lat = np.sin(2 * np.pi * Xp @ w / np.abs(w).sum() + np.pi / 4) + 0.2
-    yp = np.where(lat[uvi[:, 1]] + 0.05 * rng.standard_normal(P) > lat[uvi[:, 0]] + 0.05 * rng.standard_normal(P), 1.0, -1.0)
+    Xp, uvi, yp, lhp = make_c4()
+    D = Xp.shape[1]
     h.set_train(Xp)
     for _ in range(2):
         t0 = time.perf_counter()
-        f, lml, iters, trace, jit = h.pref_laplace(uvi, yp, np.r_[[0.5] * D, 1.0], sigma=1.0, delta_f=1e-6, max_iter=500)
+        f, lml, iters, trace, jit = h.pref_laplace(uvi, yp, np.r_[np.exp(lhp[:D]), np.exp(lhp[D]) ** 2], sigma=1.0,
+                                                   delta_f=1e-6, max_iter=500)
         dt = (time.perf_counter() - t0) * 1e3
     res["c4_gppref_n4096_p32768"] = {"ms": dt, "iters_reference_semantics": int(iters), "ms_per_iter": dt / iters, "lml": lml}
     return res

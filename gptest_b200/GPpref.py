@@ -30,6 +30,29 @@ def std_norm_pdf(x):
     return np.exp(-(x ** 2) / 2) / _sqrt_2pi
 
 
+from .GPr import squared_distance  # noqa: E402,F401  GPpref.py:13-22 (duplicate of GPr.py:4-13): same device kernel
+
+
+class SquaredExponential(object):
+    """GPpref.py:25-44.  In the reference this class is dead code: its constructor stores ``length`` and
+    ``logvar`` while its two methods read ``self.M``, ``self.sf2`` and ``self.sn2``, which nothing sets, so any
+    call raises AttributeError.  The name is kept importable with the constructor's attributes
+    (GPpref.py:27-31); the methods fail the same way.  The working kernel of this module is ``RBF`` below."""
+
+    def __init__(self, logHyp, x):
+        self.x = x
+        self.hyp = np.exp(logHyp)
+        xdim = self.x.shape[1]
+        self.length = self.hyp[0:xdim]
+        self.logvar = self.hyp[-1] ** 2
+
+    def compute_Kxx_matrix(self):
+        raise AttributeError("'SquaredExponential' object has no attribute 'M'")          # GPpref.py:34
+
+    def compute_Kxz_matrix(self, z):
+        raise AttributeError("'SquaredExponential' object has no attribute 'M'")          # GPpref.py:40
+
+
 class RBF(object):
     """Stand-in for ``GPy.kern.RBF(input_dim, ARD=True)`` (GPpref.py:109): holds ``lengthscale`` and
     ``variance`` and evaluates ``K`` on the device (r^2 clipped at 0, exact zero diagonal)."""

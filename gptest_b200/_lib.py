@@ -171,6 +171,18 @@ class Handle:
     # ---- covariance --------------------------------------------------------------------------
     # ``kind``: 0 squared exponential (the reference's only kernel, GPr.py:90-110), 1 Matern 3/2, 2 Matern 5/2.
     # It is a handle option on the C side; every wrapper sets it, so the default is always the reference's kernel.
+    def _khyp(self, khyp, extra=2):
+        """khyp as fp64 with d + extra entries per row; the C side reads khyp[.. d + extra - 1] unconditionally, so a
+        vector that does not fit the input dimension is refused here (the reference fails with a numpy
+        broadcasting ValueError in the same situation)."""
+        khyp = as_f64(khyp)
+        if not hasattr(self, 'd'):
+            raise ValueError('no training data on this handle: call set_train first')
+        if khyp.shape[-1] != self.d + extra:
+            raise ValueError('hyper-parameter vector has %d entries, input dimension %d needs %d'
+                             % (khyp.shape[-1], self.d, self.d + extra))
+        return khyp
+
     def _kind(self, kind):
         if kind != self._cov_kind:
             self.check(self.lib.gpb_set_option(self.h, b'cov_kind', int(kind)))
@@ -178,19 +190,19 @@ class Handle:
 
     def kxx(self, khyp, flags=0, kind=0):
         self._kind(kind)
-        khyp = as_f64(khyp)
+        khyp = self._khyp(khyp)
         out = np.empty((self.n, self.n))
         self.check(self.lib.gpb_se_ard_kxx(self.h, _dp(khyp), out.ctypes.data_as(C.c_void_p), 0, flags))
         return out
 
     def kxx_dev(self, khyp, dev_ptr, flags=0, kind=0):
         self._kind(kind)
-        khyp = as_f64(khyp)
+        khyp = self._khyp(khyp)
         self.check(self.lib.gpb_se_ard_kxx(self.h, _dp(khyp), C.c_void_p(dev_ptr), 1, flags))
 
     def kxz(self, khyp, Z, kind=0):
         self._kind(kind)
-        khyp = as_f64(khyp)
+        khyp = self._khyp(khyp)
         Z = as_f64(Z)
         Z = Z.reshape(len(Z), -1)
         out = np.empty((self.n, Z.shape[0]))
@@ -207,7 +219,7 @@ class Handle:
     # ---- regression ----------------------------------------------------------------------------
     def gpr_nlml(self, khyp, mean=0.0, want_grad=False, kind=0):
         self._kind(kind)
-        khyp = as_f64(khyp)
+        khyp = self._khyp(khyp)
         val = C.c_double()
         info = C.c_int32()
         grad = np.empty(len(khyp)) if want_grad else None
@@ -219,7 +231,7 @@ class Handle:
 
     def gpr_predict(self, khyp, Z, mean=0.0, kind=0):
         self._kind(kind)
-        khyp = as_f64(khyp)
+        khyp = self._khyp(khyp)
         Z = as_f64(Z)
         Z = Z.reshape(len(Z), -1)
         m = Z.shape[0]
@@ -232,7 +244,7 @@ class Handle:
 
     def gpr_nlml_batched(self, khyp, mean=0.0, want_grad=False, kind=0):
         self._kind(kind)
-        khyp = as_f64(khyp)
+        khyp = self._khyp(np.atleast_2d(as_f64(khyp)))
         B, p = khyp.shape
         val = np.empty(B)
         info = np.zeros(B, dtype=np.int32)
@@ -320,7 +332,7 @@ def _pref_laplace(self, uvi, y, khyp, sigma=1.0, delta_f=1e-6, max_iter=1000, gr
     """PreferenceGaussianProcess.calc_laplace on the device: returns (f (n,), lml, iters, trace, jitter)."""
     uvi = np.ascontiguousarray(uvi, dtype=np.int64).reshape(-1, 2)
     y = as_f64(y).reshape(-1)
-    khyp = as_f64(khyp)
+    khyp = self._khyp(khyp, extra=1)
     P = uvi.shape[0]
     assert y.shape[0] == P
     f = np.zeros(self.n) if f0 is None else as_f64(f0).reshape(-1).copy()
@@ -352,7 +364,7 @@ def _pref_derivatives(self, uvi, y, f, sigma=1.0, grad_mode=0):
 
 def _gpc_laplace(self, y, khyp, link=0, delta_f=1e-6, max_iter=100, f0=None):
     y = as_f64(y).reshape(-1)
-    khyp = as_f64(khyp)
+    khyp = self._khyp(khyp, extra=1)
     f = np.zeros(self.n) if f0 is None else as_f64(f0).reshape(-1).copy()
     lml = C.c_double()
     iters = C.c_int32()

@@ -185,8 +185,12 @@ int gpb_create(int device, gpb_handle** out) {
     tile_potrf_init();
   } catch (const gpb::Error& e) {
     g_create_error = e.msg;
-    delete h;
+    gpb_destroy(h);               // releases whatever streams / events were created before the failure
     return -2;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    gpb_destroy(h);
+    return -3;
   }
   *out = h;
   return 0;

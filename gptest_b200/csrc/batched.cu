@@ -118,6 +118,9 @@ extern "C" int gpb_gpr_nlml_batched(gpb_handle* h, const double* khyp, int64_t B
   } catch (const gpb::Error& e) {
     h->err = e.msg;
     return -2;
+  } catch (const std::exception& e) {      // bad_alloc etc. must not unwind through the C boundary
+    h->err = e.what();
+    return -3;
   }
   return 0;
 }

@@ -95,7 +95,8 @@ int gpb_gpr_predict(gpb_handle* h, const double* khyp, double mean, const double
                     double* fz, double* cov, int32_t* info);
 /* B independent evaluations of compute_likelihood on the same (X, y) with different
  * hyper-parameters (the grid / multi-start fits GP_parameter_fit.py:32-33 runs one by one).
- * loghyp: B x (d+2) host; nlml: B host; grad: B x (d+2) host or NULL; info: B host. */
+ * khyp: B x (d+2) host, NATURAL parameters [l_1..l_d, sf2, sn2] per row (as for gpb_gpr_nlml); nlml: B host;
+ * grad: B x (d+2) host or NULL, w.r.t. the LOG hyper-parameters; info: B host. */
 int gpb_gpr_nlml_batched(gpb_handle* h, const double* khyp, int64_t B, double mean,
                          double* nlml, double* grad, int32_t* info);
 

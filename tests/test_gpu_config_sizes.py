@@ -1,0 +1,116 @@
+"""CUDA vs the CPU oracle AT the BASELINE.json config sizes (SURVEY section 4 plan (ii), (iv)).
+
+The other GPU test files compare against the oracle at sizes it finishes in a second and check the
+full sizes through properties; here the oracle itself is run at C2 / C3 / C4 / C5 size (tens of seconds
+of host BLAS each) on exactly the inputs bench.py times (bench_configs.py).
+
+Tolerances (BASELINE.json north_star): NLML 1e-8 relative, posterior mean 1e-9 relative (to the scale of
+the mean), variance 1e-9 of sigma_f^2, Laplace mode 1e-6 after the same iteration count.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import bench_configs as cfg
+from oracle import gpr_oracle, gppref_oracle, gpc_oracle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c2_fit_and_predict_match_oracle_at_n16384(handle):
+    """GPr.py:57-69 / :45-54 at N=16384, D=8, M=1024 (Cholesky form of the oracle: SURVEY H3)."""
+    X, y, Z, lh = cfg.make_c2()
+    ref_nlml = float(gpr_oracle.nlml_chol(lh, X, y))
+    ref_mean, ref_var = gpr_oracle.predict_chol(lh, X, y, Z)
+    kh = cfg.khyp_of(lh)
+    handle.set_train(X, y)
+    v = handle.gpr_nlml(kh)
+    assert abs(v - ref_nlml) <= 1e-8 * abs(ref_nlml), (v, ref_nlml)
+    fz, cov = handle.gpr_predict(kh, Z)
+    sf2 = kh[-2]
+    assert np.abs(fz - ref_mean).max() <= 1e-9 * np.abs(ref_mean).max()
+    assert np.abs(cov - ref_var).max() <= 1e-9 * sf2
+    # the drop-in class gives the same numbers (host buffers uploaded by the constructor)
+    from gptest_b200 import GPr
+    gp = GPr.GaussianProcess(lh, 0, 0, "SE", "zero", "zero", X, y)
+    out = gp.compute_likelihood(lh)
+    assert out.shape == (1, 1) and abs(out[0, 0] - ref_nlml) <= 1e-8 * abs(ref_nlml)
+    # value + gradient at full size: value equal to the plain fit, gradient finite and consistent between calls
+    v2, g2 = handle.gpr_nlml(kh, want_grad=True)
+    assert abs(v2 - ref_nlml) <= 1e-8 * abs(ref_nlml)
+    assert np.isfinite(g2).all() and g2.shape == (10,)
+
+
+def test_c3_gpc_matches_oracle_at_n4096_and_n8192(handle):
+    """R&W Alg. 3.1 (GPc.py intent; parity unpinned): full convergence at N=4096, the first two Newton steps at
+    the C3 size N=8192 (trace and mode after the same count)."""
+    for n, cap in ((4096, 100), (8192, 2)):
+        X, y, Z, lh = cfg.make_c3(n=n)
+        D = X.shape[1]
+        of, olml, st = gpc_oracle.calc_laplace(X, y, lh, max_iter=cap, return_state=True)
+        kh = np.concatenate([np.exp(lh[:D]), [np.exp(lh[D]) ** 2]])
+        handle.set_train(X)
+        f, lml, iters, trace, jit = handle.gpc_laplace(y, kh, link=0, delta_f=1e-6, max_iter=cap)
+        assert iters == st['it'] and jit == st['eps'], (iters, st['it'], jit, st['eps'])
+        otr = np.array(st['trace'])
+        assert np.abs(trace[:, 0] - otr[:, 0]).max() < 1e-6
+        assert np.abs(trace[:, 1] - otr[:, 1]).max() <= 1e-8 * np.abs(otr[:, 1]).max()
+        assert np.abs(f - of).max() < 1e-6
+        assert abs(lml - olml) <= 1e-8 * abs(olml), (lml, olml)
+
+
+def test_c4_gppref_matches_oracle_at_n4096_p32768(handle):
+    """GPpref.py:112-157 at the C4 size: 8 iterations of the reference-semantics loop (last-write-wins gradient,
+    sigma frozen at 1, quarter log-determinant), same count on both sides."""
+    X, uvi, y, lh = cfg.make_c4()
+    D = X.shape[1]
+    cap = 8
+    of, olml, otrace = gppref_oracle.calc_laplace(X, uvi, y, lh, delta_f=0.0, max_iter=cap, return_trace=True)
+    otrace = np.array(otrace)
+    kh = np.concatenate([np.exp(lh[:D]), [np.exp(lh[D]) ** 2]])
+    handle.set_train(X)
+    f, lml, iters, trace, jit = handle.pref_laplace(uvi, y, kh, sigma=1.0, delta_f=0.0, max_iter=cap)
+    assert iters == cap == len(otrace)
+    assert jit == 1e-6
+    assert np.abs(f - of[:, 0]).max() < 1e-6
+    assert abs(lml - olml) <= 1e-8 * abs(olml), (lml, olml)
+    assert np.abs(trace[:, 0] - otrace[:, 0]).max() < 1e-6
+    assert np.abs(trace[:, 1] - otrace[:, 1]).max() <= 1e-8 * np.abs(otrace[:, 1]).max()
+
+
+def test_c5_grid_rows_match_oracle(handle):
+    """16 of the 1024 problems of the sweep (four corners of the 32x32 grid + 12 seeded picks; sigma_f up to 30
+    with sigma_n = 0.25: cond ~ 1e7) against GPr.py:57-69, evaluated inside ONE batched call of all 1024."""
+    X, Y, lhs = cfg.make_c5()
+    rows = [0, 31, 1024 - 32, 1023] + sorted(np.random.default_rng(5).choice(1024, 12, replace=False).tolist())
+    kh = np.array([cfg.khyp_of(l) for l in lhs])
+    handle.set_train(X, Y)
+    vals, info = handle.gpr_nlml_batched(kh)
+    assert (info == 0).all()
+    for r in rows:
+        ref = float(gpr_oracle.nlml(lhs[r], X, Y)[0, 0])
+        assert abs(vals[r] - ref) <= 1e-8 * abs(ref), (r, vals[r], ref)
+    # a row evaluated alone equals the same row inside the batch to the last few bits
+    for r in rows[:4]:
+        one = handle.gpr_nlml(kh[r])
+        assert abs(one - vals[r]) <= 1e-11 * abs(one)
+
+
+def test_sweep_nlml_two_ranks_equal_one_rank_bitwise():
+    """gptest_b200.sweep.sweep_nlml with its default CUDA evaluator over NCCL on two GPUs returns bit for bit
+    what one rank returns (tests/_sweep_nccl_worker.py); needs two devices."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    env = dict(os.environ)
+    env.pop("LOCAL_RANK", None)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29617",
+                        os.path.join(ROOT, "tests", "_sweep_nccl_worker.py")],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "SWEEP_NCCL_OK" in r.stdout

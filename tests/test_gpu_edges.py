@@ -199,3 +199,70 @@ def test_two_handles_are_independent(handle):
         assert np.abs(ga - gpr_oracle.nlml_grad(lha, Xa, ya)).max() <= 1e-7 * max(1.0, np.abs(ga).max())
     finally:
         other.close()
+
+
+def test_far_apart_points_underflow_to_zero_like_numpy(handle):
+    """Scaled distances of several thousand (short length scales, line-search excursions): x = -r^2/2 down to
+    -5e7.  numpy's exp returns exactly 0 there (GPr.py:102); the table exp must too - before the clamp its
+    integer exponent wrapped and K held huge or negative entries."""
+    rng = np.random.default_rng(7)
+    X = 100.0 * rng.random((300, 2))
+    y = rng.standard_normal(300)
+    for ell in (0.01, 0.004, 0.1):
+        lh = np.log([ell, ell, 1.0, 0.1])
+        handle.set_train(X, y)
+        K = handle.kxx(natural(lh))
+        ref = gpr_oracle.kxx(lh, X)
+        assert np.isfinite(K).all() and (K >= 0).all()
+        assert np.abs(K - ref).max() <= 2e-14
+        off = K[~np.eye(300, dtype=bool)]
+        assert (off[ref[~np.eye(300, dtype=bool)] == 0.0] == 0.0).all()
+        v = handle.gpr_nlml(natural(lh))
+        r = float(gpr_oracle.nlml(lh, X, y)[0, 0])
+        assert abs(v - r) <= 1e-8 * abs(r)
+        vg, g = handle.gpr_nlml(natural(lh), want_grad=True)
+        assert np.isfinite(g).all() and abs(vg - r) <= 1e-8 * abs(r)
+    # Matern kernels go through the same exp with x = -a
+    handle.set_train(X, y)
+    K = handle.kxx(natural(np.log([1e-4, 1e-4, 1.0, 0.1])), kind=1)
+    assert np.isfinite(K).all() and (K[~np.eye(300, dtype=bool)] == 0.0).all() and np.abs(np.diag(K) - 1.01).max() < 1e-15
+
+
+def test_hyperparameter_vector_of_the_wrong_length_is_refused(handle):
+    """A log_hyp that does not fit the input dimension (e.g. the 3-entry demo vector with 2-D X): the reference
+    raises a numpy broadcasting ValueError; the binding must not read past the vector."""
+    rng = np.random.default_rng(3)
+    X = rng.random((40, 2))
+    y = rng.standard_normal(40)
+    handle.set_train(X, y)
+    bad = np.array([0.5, 1.0, 0.01])
+    for call in (lambda: handle.gpr_nlml(bad), lambda: handle.gpr_predict(bad, X[:3]), lambda: handle.kxx(bad),
+                 lambda: handle.kxz(bad, X[:3]), lambda: handle.gpr_nlml_batched(np.tile(bad, (4, 1))),
+                 lambda: handle.gpc_laplace(np.sign(y), np.array([0.5, 1.0])),
+                 lambda: handle.pref_laplace(np.array([[0, 1]]), np.array([1.0]), np.array([0.5, 0.5, 1.0, 1.0]))):
+        with pytest.raises(ValueError):
+            call()
+    from gptest_b200 import GPr
+    gp = GPr.GaussianProcess(np.log([1.0, 1.0, 0.1]), 0, 0, "SE", "zero", "zero", X, y)
+    with pytest.raises(ValueError):
+        gp.compute_likelihood(np.log([1.0, 1.0, 0.1]))
+    with pytest.raises(ValueError):
+        gp.compute_prediction(X[:3])
+
+
+@pytest.mark.parametrize('opt,val', [('potrf_variant', 0), ('split_tiles', 0), ('lookahead', 0)])
+def test_alternative_kernel_paths_agree_with_the_default(handle, opt, val):
+    """The kernels kept behind options (the previous register-resident diagonal-tile kernel, 128x128 CTA tiles,
+    the plain order) factor the same matrix to rounding."""
+    rng = np.random.default_rng(11)
+    n = 1536
+    M = rng.standard_normal((n, n))
+    A = M @ M.T / n + np.eye(n)
+    L0 = handle.potrf(A)
+    handle.set_option(opt, val)
+    try:
+        L1 = handle.potrf(A)
+    finally:
+        handle.set_option(opt, {'potrf_variant': 2, 'split_tiles': 1, 'lookahead': 1}[opt])
+    assert np.abs(L0 - np.linalg.cholesky(A)).max() < 1e-12
+    assert np.abs(L1 - L0).max() < 1e-12

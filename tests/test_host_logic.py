@@ -127,3 +127,17 @@ def test_block_append_model(n0, m):
     assert np.abs(L - L_full).max() < 1e-12 and np.abs(z - z_full).max() < 1e-11
     nlml = 0.5 * z @ z + np.sum(np.log(np.diag(L))) + n1 * np.log(2 * np.pi) / 2
     assert abs(nlml - gpr_oracle.nlml_chol(lh, x, y)) < 1e-9 * max(1.0, abs(nlml))
+
+
+def test_gppref_module_level_names_of_the_reference():
+    """GPpref.py defines std_norm_pdf, squared_distance, SquaredExponential, PrefProbit and
+    PreferenceGaussianProcess at module level; `from GPpref import squared_distance` must keep working."""
+    import numpy as np
+    from gptest_b200 import GPpref
+    for name in ('std_norm_pdf', 'squared_distance', 'SquaredExponential', 'PrefProbit', 'PreferenceGaussianProcess'):
+        assert hasattr(GPpref, name), name
+    se = GPpref.SquaredExponential(np.log([0.5, 0.5, 1.0]), np.zeros((4, 2)))       # GPpref.py:26-31
+    assert se.length.shape == (2,) and abs(se.logvar - 1.0) < 1e-15
+    import pytest
+    with pytest.raises(AttributeError):                                             # GPpref.py:34 reads self.M
+        se.compute_Kxx_matrix()
