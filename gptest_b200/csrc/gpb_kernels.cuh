@@ -61,10 +61,12 @@ struct TilePotrfArgs {
   int64_t diag_batch_stride;
   int* info;                // per batch: first failing pivot (1-based global index), 0 = ok
   int pdl;                  // launch with programmatic stream serialisation
+  long long* dbg;           // optional (tools/micro/tp3_bench.cu): clock64() of the phase boundaries, per warp; normally null
 };
 void launch_tile_potrf_inv(TilePotrfArgs a, int batch, cudaStream_t st);
 void tile_potrf_init();
-void tile_potrf_set_variant(int v);
+void tile_potrf_set_variant(int v);          // 3 (default): blocked in-CTA kernel (tile_potrf3.cu)  2: register-resident sweep
+void tile_potrf_set_refine(int on);          // variant 3: corrected (default) or bare rsqrt pivots
 
 // ---------------------------------------------------------------------------------------
 // SE-ARD covariance assembly

@@ -36,124 +36,6 @@ constexpr int TP_THREADS = 256;
 constexpr int TP_PITCH = TILE + 1;
 constexpr int TP_SMEM = TILE * TP_PITCH * 8;
 
-template <int JB>
-__device__ __forceinline__ void potrf_block_steps(double (&c)[8][8], double (&dg)[8], double (*v)[TILE], int* fail,
-                                                  const int tr, const int tc) {
-  const bool ge = (tr >= tc);                            // inside a diagonal 16x16 block: on or below the diagonal
-  for (int jj = 0; jj < 16; ++jj) {
-    const int j = 16 * JB + jj;
-    double* vb = v[j & 1];
-    if (tc == jj) {
-      const double ajj = dg[JB];
-      if (tr == 0 && !(ajj > 0.0)) atomicMin(fail, j);       // also catches NaN
-      // d = sqrt(ajj), invd = 1/d from one rsqrt and one correction step each (<= 1 ulp)
-      // d = sqrt(ajj) and 1/d from one rsqrt plus one correction step each (<= 1 ulp).  Dropping the
-      // corrections saves 4 % of this kernel but raises the noise floor of the ill-conditioned Laplace
-      // systems (K + 1e-6 I) above 1e-9 - measured, not worth it.
-      const double r0 = rsqrt(ajj);
-      double d = ajj * r0;
-      d = fma(0.5 * r0, fma(-d, d, ajj), d);
-      const double invd = fma(r0, fma(-d, r0, 1.0), r0);
-#pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        const int r = tr + 16 * a;
-        if (r != j) {
-          c[a][JB] *= invd;
-          vb[r] = c[a][JB];
-        } else {
-          c[a][JB] = d;
-          vb[r] = invd;
-        }
-      }
-    }
-    __syncthreads();
-    // Cell (a,b) takes part iff its column c = tc+16b is right of j and its row r = tr+16a is an
-    // inverse row (r <= j) or a factor row (r >= c).  ncu showed the per-cell predicates, not the
-    // FP64 work, bound this kernel (2/3 of the issued instructions): so the FMAs are unconditional
-    // and inactivity is a ZERO MULTIPLIER chosen by a handful of selects per column
-    // (c - 0*x == c exactly); cells that can never be active for this JB are skipped statically.
-    double vr[8], vc[8];
-#pragma unroll
-    for (int a = 0; a < 8; ++a) vr[a] = vb[tr + 16 * a];
-#pragma unroll
-    for (int b = JB; b < 8; ++b) vc[b] = vb[tc + 16 * b];
-    const bool p_row = (tr <= jj);                       // row block JB: inverse row?
-    vc[JB] = (tc > jj) ? vc[JB] : 0.0;                   // column block JB: right of j?
-    const double vr_inv = p_row ? vr[JB] : 0.0;          // rows of block JB against columns of later blocks
-    double vr_dg[8];                                     // multiplier of the cells with a == b
-#pragma unroll
-    for (int a = JB; a < 8; ++a) vr_dg[a] = (ge || (a == JB && p_row)) ? vr[a] : 0.0;
-#pragma unroll
-    for (int b = JB; b < 8; ++b) {
-      dg[b] = fma(-vc[b], vc[b], dg[b]);
-#pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        if (a < JB) c[a][b] = fma(-vr[a], vc[b], c[a][b]);                 // inverse rows of earlier blocks
-        else if (a == b) c[a][b] = fma(-vr_dg[a], vc[b], c[a][b]);         // diagonal 16x16 block
-        else if (a > b) c[a][b] = fma(-vr[a], vc[b], c[a][b]);             // factor rows below
-        else if (a == JB) c[a][b] = fma(-vr_inv, vc[b], c[a][b]);          // a == JB < b: inverse rows of this block
-        // JB < a < b: neither an inverse row yet nor a factor row of that column
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(TP_THREADS, 1) tile_potrf_inv_kernel(const TilePotrfArgs p) {
-  extern __shared__ double S[];                 // [128][129] staging for the outputs
-  __shared__ double v[2][TILE];
-  __shared__ int fail;
-  const int t = threadIdx.x;
-  const int tc = t >> 4, tr = t & 15;            // the 16 owners of a column share one warp: 7 warps skip the scaling branch
-  const int batch = blockIdx.x;
-  double* Ab = p.A + batch * p.a_batch_stride + static_cast<int64_t>(p.k) * TILE * p.lda + p.k * TILE;
-
-  pdl_trigger();
-  if (t == 0) fail = TILE;
-  pdl_wait();                                    // the tile was updated by the preceding kernels of the stream
-  double c[8][8], dg[8];
-#pragma unroll
-  for (int a = 0; a < 8; ++a)
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      const int r = tr + 16 * a, cc = tc + 16 * b;
-      c[a][b] = (r >= cc) ? Ab[static_cast<int64_t>(r) * p.lda + cc] : 0.0;
-    }
-#pragma unroll
-  for (int b = 0; b < 8; ++b) {
-    const int cc = tc + 16 * b;
-    dg[b] = Ab[static_cast<int64_t>(cc) * p.lda + cc];
-  }
-  __syncthreads();
-
-  potrf_block_steps<0>(c, dg, v, &fail, tr, tc);
-  potrf_block_steps<1>(c, dg, v, &fail, tr, tc);
-  potrf_block_steps<2>(c, dg, v, &fail, tr, tc);
-  potrf_block_steps<3>(c, dg, v, &fail, tr, tc);
-  potrf_block_steps<4>(c, dg, v, &fail, tr, tc);
-  potrf_block_steps<5>(c, dg, v, &fail, tr, tc);
-  potrf_block_steps<6>(c, dg, v, &fail, tr, tc);
-  potrf_block_steps<7>(c, dg, v, &fail, tr, tc);
-
-#pragma unroll
-  for (int a = 0; a < 8; ++a)
-#pragma unroll
-    for (int b = 0; b < 8; ++b) S[(tr + 16 * a) * TP_PITCH + tc + 16 * b] = c[a][b];
-  __syncthreads();
-
-  double* Dk = p.Dinv + batch * p.d_batch_stride + static_cast<int64_t>(p.k) * TILE * TILE;
-  for (int idx = t; idx < TILE * TILE; idx += TP_THREADS) {
-    const int r = idx >> 7, cc = idx & 127;
-    if (cc <= r) Ab[static_cast<int64_t>(r) * p.lda + cc] = S[r * TP_PITCH + cc];
-    // W[r][cc] = (L^-T)[cc][r]: strict upper cell S[cc][r] for cc < r, 1/L_rr on the diagonal
-    double w = 0.0;
-    if (cc < r) w = S[cc * TP_PITCH + r];
-    else if (cc == r) w = 1.0 / S[r * TP_PITCH + r];
-    Dk[idx] = w;
-  }
-  if (t < TILE) p.diag[batch * p.diag_batch_stride + p.k * TILE + t] = S[t * TP_PITCH + t];
-  if (t == 0 && fail < TILE) atomicCAS(p.info + batch, 0, p.k * TILE + fail + 1);
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // Variant 2 (the default): the owners of column j+1 run its pivot chain in the MIDDLE of step j - right after the
 // cells of their own column block have been updated and before the rest of the sweep - so that the rsqrt chain is
@@ -300,20 +182,28 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tile_potrf_inv_kernel2(const Ti
   if (t == 0 && fail < TILE) atomicCAS(p.info + batch, 0, p.k * TILE + fail + 1);
 }
 
-static int g_potrf_variant = 2;       // 2: pivot inside the step (default), 0: pivot at the top of the step
-void tile_potrf_set_variant(int v) { g_potrf_variant = v; }
+// variant 3 (default): blocked inside the CTA, warp-shuffle base case + DMMA block products (tile_potrf3.cu)
+// variant 2          : the register-resident sweep above (kept as a cross-check: tests/test_gpu_edges.py)
+void tile_potrf3_init();
+void launch_tile_potrf3(const TilePotrfArgs& a, int batch, cudaStream_t st, bool pdl, bool refine);
+
+static int g_potrf_variant = 3;
+static int g_potrf_refine = 1;        // variant 3: one correction step on rsqrt for 1/d and d (<= 1 ulp) or the bare rsqrt
+void tile_potrf_set_variant(int v) { g_potrf_variant = (v == 2) ? 2 : 3; }
+void tile_potrf_set_refine(int on) { g_potrf_refine = on != 0; }
 
 void tile_potrf_init() {
-  GPB_CUDA(cudaFuncSetAttribute(tile_potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM));
   GPB_CUDA(cudaFuncSetAttribute(tile_potrf_inv_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM));
+  tile_potrf3_init();
 }
 
 void launch_tile_potrf_inv(TilePotrfArgs a, int batch, cudaStream_t st) {
+  const bool pdl = g_pdl != 0 && a.pdl != 0;
   if (g_potrf_variant == 2) {
-    launch_chain(tile_potrf_inv_kernel2, dim3(batch), dim3(TP_THREADS), TP_SMEM, st, g_pdl != 0 && a.pdl != 0, a);
+    launch_chain(tile_potrf_inv_kernel2, dim3(batch), dim3(TP_THREADS), TP_SMEM, st, pdl, a);
     return;
   }
-  launch_chain(tile_potrf_inv_kernel, dim3(batch), dim3(TP_THREADS), TP_SMEM, st, g_pdl != 0 && a.pdl != 0, a);
+  launch_tile_potrf3(a, batch, st, pdl, g_potrf_refine != 0);
 }
 
 }  // namespace gpb
