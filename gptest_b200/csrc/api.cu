@@ -231,6 +231,7 @@ int gpb_set_option(gpb_handle* h, const char* name, int64_t value) {
   else if (!strcmp(name, "nb_tiles")) h->nb_tiles = static_cast<int>(value < 0 ? 0 : (value > 8 ? 8 : value));
   else if (!strcmp(name, "batch_chunk")) h->batch_chunk = value;
   else if (!strcmp(name, "small_tile_threshold")) h->small_tile_threshold = value;
+  else if (!strcmp(name, "thin_tile_max")) h->thin_tile_max = value;
   else if (!strcmp(name, "split_tiles")) h->split_tiles = value != 0;
   else if (!strcmp(name, "persistent_waves")) dmma_gemm_set_persistent(static_cast<int>(value));
   else if (!strcmp(name, "stagger")) dmma_gemm_set_stagger(static_cast<int>(value));

@@ -61,6 +61,7 @@ void make_tile_maps(TileMaps* maps, const double* base, int64_t cols, int64_t ro
                     int64_t row_pitch, int64_t batch_pitch) {
   make_tensor_map(&maps->m128, base, cols, rows, batch, row_pitch, batch_pitch, 128);
   make_tensor_map(&maps->m64, base, cols, rows, batch, row_pitch, batch_pitch, 64);
+  make_tensor_map(&maps->m32, base, cols, rows, batch, row_pitch, batch_pitch, 32);
 }
 
 void finalize_factor_mat(FactorMat& m) {
@@ -116,6 +117,20 @@ struct Sweep {
   void launch(const GemmArgs& a, const TileMaps& ma, const TileMaps& mb, cudaStream_t st) {
     const int n128 = gemm_region_tiles(a);
     if (n128 <= 0) return;
+    if (!big_tiles && a.tri && a.j1 - a.j0 == 1 && static_cast<int64_t>(n128) * m.batch <= h->thin_tile_max) {
+      // one tile column with few tiles: the update of the next panel's column, i.e. the critical chain of a small
+      // matrix.  A lone 64x64 CTA-tile needs 4.2 us of its SM's FP64 pipe for K = 128; 32 x 64 tiles put the same work
+      // on four times as many SMs (rectangular region: the diagonal tile is computed whole, its upper half is unused).
+      GemmArgs b = a;
+      b.tri = 0;
+      b.i0 = 4 * (a.j0 + a.i_off);
+      const int r32 = (a.rows_total + 31) / 32;
+      b.R = 4 * a.R < r32 ? 4 * a.R : r32;
+      b.j0 = 2 * a.j0; b.j1 = 2 * a.j1; b.i_off = 0;
+      launch_dmma_gemm(ma.m32, mb.m64, b, m.batch, st, 3264);
+      ++h->launches;
+      return;
+    }
     if (!big_tiles && static_cast<int64_t>(n128) * m.batch < h->small_tile_threshold) {
       launch_dmma_gemm(ma.m64, mb.m64, gemm_args_to_64(a), m.batch, st, 64);
     } else if (h->split_tiles) {
@@ -137,6 +152,16 @@ struct Sweep {
     a.epi = 0;
     const int n128 = gemm_region_tiles(a);
     if (n128 <= 0) return;
+    if (static_cast<int64_t>(n128) * m.batch <= h->thin_tile_max) {
+      // few rows (the panel of a small matrix, on the critical chain): 32-row CTA-tiles, four per 128-row tile
+      GemmArgs b = a;
+      b.i0 = 4 * a.i0;
+      const int r32 = (a.rows_total + 31) / 32;
+      b.R = 4 * a.R < r32 ? 4 * a.R : r32;
+      launch_dmma_gemm(m.mapA.m32, m.mapD.m128, b, m.batch, st, 32128);
+      ++h->launches;
+      return;
+    }
     if (static_cast<int64_t>(n128) * m.batch < h->small_tile_threshold) {
       GemmArgs b = a;
       b.i0 = 2 * a.i0;

@@ -285,6 +285,10 @@ void dmma_gemm_init() {
                                 smem_bytes(64, 128)));
   GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<128, 64, 2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 smem_bytes(128, 64)));
+  GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<32, 128, 2, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                smem_bytes(32, 128)));
+  GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<32, 64, 2, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                smem_bytes(32, 64)));
   int dev = 0, sms = 0;
   GPB_CUDA(cudaGetDevice(&dev));
   GPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -329,6 +333,14 @@ void launch_dmma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmArgs
     // region in 128-tiles, each cut into two 128 x 64 CTA-tiles; two CTAs share an SM
     // (mapA with 128-row boxes, mapB with 64-row boxes)
     launch_chain(dmma_gemm_nt_kernel<128, 64, 2, 2, 2>, grid_for(2 * ntiles, 2), dim3(4 * 32), smem_bytes(128, 64), st, pdl,
+                 mapA, mapB, a);
+  } else if (tile == 32128) {
+    // 32 x 128, 8 warps of 16 x 32: rows in units of 32, columns in units of 128 (the in-place panel TRSM of a small matrix)
+    launch_chain(dmma_gemm_nt_kernel<32, 128, 2, 4, 2>, grid_for(ntiles, 2), dim3(8 * 32), smem_bytes(32, 128), st, pdl,
+                 mapA, mapB, a);
+  } else if (tile == 3264) {
+    // 32 x 64, 8 warps of 16 x 16: rows in units of 32, columns in units of 64 (single-column update on the critical chain)
+    launch_chain(dmma_gemm_nt_kernel<32, 64, 2, 4, 3>, grid_for(ntiles, 3), dim3(8 * 32), smem_bytes(32, 64), st, pdl,
                  mapA, mapB, a);
   } else if (tile == 64) {
     // A launch that leaves SMs with a single CTA is latency bound (one warp per scheduler: 1.34 us per 16-deep k

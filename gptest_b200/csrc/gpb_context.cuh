@@ -75,6 +75,7 @@ struct gpb_handle {
                                  // (measured: N=16384 B=4 47.5 vs 50.2 ms/fit, N=4096 B=8 1.08 vs 1.20; 1024x2048 neutral)
   int split_tiles = 1;           // big launches: 1 = 128x64 CTAs, two per SM (finer grain: the look-ahead panel
                                  // kernels get SMs sooner, N=16384: 49.7 vs 52.4 ms); 0 = 128x128, one per SM
+  int64_t thin_tile_max = 74;    // panel TRSM / single-column update launches with at most this many 128-tiles use 32-row CTA-tiles
   int64_t small_tile_threshold = 2400;  // launches with fewer 128-tiles than this use 64-tiles (tuned: r01_tune_potrf.json)
 
   // training data (GPr.py:25-26 keeps trainInput / trainTarget on the object)

@@ -34,8 +34,8 @@ struct GemmArgs {
 int gemm_region_tiles(const GemmArgs& a);       // host: number of tiles of the region
 // one tensor map per tile edge: the TMA box height is part of the map
 struct TileMaps {
-  CUtensorMap m128, m64;
-  const CUtensorMap& get(int tile) const { return tile == 128 ? m128 : m64; }
+  CUtensorMap m128, m64, m32;
+  const CUtensorMap& get(int tile) const { return tile == 128 ? m128 : (tile == 64 ? m64 : m32); }
 };
 void launch_dmma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmArgs a, int batch,
                       cudaStream_t st, int tile);
