@@ -94,6 +94,21 @@ def cpu_fit_seconds(n, log_hyp, X, y):
     return time.perf_counter() - t0, float(v[0, 0])
 
 
+_BLAS_LIMIT = None
+
+
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs must run on all host cores, so the
+    BLAS pool is resized explicitly.  Returns the number of threads in use."""
+    global _BLAS_LIMIT
+    try:
+        from threadpoolctl import threadpool_limits
+        _BLAS_LIMIT = threadpool_limits(limits=os.cpu_count() or 1, user_api='blas')
+    except Exception:
+        pass
+    return blas_threads()
+
+
 def blas_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -108,6 +123,7 @@ def blas_threads():
 
 def cpu_baseline(budget_s=20.0):
     """The reference's arithmetic (oracle port of GPr.py:57-69) on the host cores, bounded sample."""
+    use_all_host_cores()
     X, y, _, lh = make_c2()
     t1024, _ = cpu_fit_seconds(1024, lh, X, y)
     t1024, _ = cpu_fit_seconds(1024, lh, X, y)
@@ -120,7 +136,18 @@ def cpu_baseline(budget_s=20.0):
     return {"value": 1.0 / (t * scale), "unit": "fits/s", "cores": blas_threads(), "kind": "port",
             "sample": "one compute_likelihood at N=%d (first %d points of the workload), %.2f s; "
                       "extrapolated x(16384/%d)^3 = %.0f for N=16384" % (ns, ns, t, ns, scale),
-            "host_cpus": os.cpu_count(), "other_configs": cpu_other_configs()}
+            "host_cpus": os.cpu_count(), "other_configs": cpu_other_configs(),
+            "measured_full_size": measured_full_size_record()}
+
+
+def measured_full_size_record():
+    """One REAL N=16384 compute_likelihood of the CPU port, measured once on a GPU box's host by
+    `bench.py --impl reference --ref-full` (about four minutes: too long for the default run) and kept under profiles/."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r02_cpu_full_size.json")))
+        return {k: rec[k] for k in ("value", "unit", "ms_per_step", "cpu_baseline")} | {"source": "profiles/r02_cpu_full_size.json (not measured in this run)"}
+    except Exception:
+        return None
 
 
 def cpu_other_configs():
@@ -158,33 +185,44 @@ def cpu_other_configs():
 
 
 def run_reference(args, rank, world):
+    """The reference's own CPU arithmetic on the host cores: rank 0 only.  Default: every step is one
+    compute_likelihood at the largest N in (1024, 2048, 4096) for which all steps fit ~150 s, extrapolated cubically
+    to N=16384 and labelled so; --ref-full: steps at the real N=16384 (about 4 minutes each, 20 GiB)."""
     if rank != 0:
         return
+    cores = use_all_host_cores()
     X, y, _, lh = make_c2()
     steps, warm = args.steps, args.warmup
-    t1024, _ = cpu_fit_seconds(1024, lh, X, y)
-    t1024, _ = cpu_fit_seconds(1024, lh, X, y)
-    ns = 1024
-    for cand in (2048, 4096):
-        if t1024 * (cand / 1024.0) ** 3 * (steps + warm) <= 150.0:
-            ns = cand
+    if args.ref_full:
+        ns = N_FIT
+    else:
+        t1024, _ = cpu_fit_seconds(1024, lh, X, y)
+        t1024, _ = cpu_fit_seconds(1024, lh, X, y)
+        ns = 1024
+        for cand in (2048, 4096):
+            if t1024 * (cand / 1024.0) ** 3 * (steps + warm) <= 150.0:
+                ns = cand
     for _ in range(warm):
         cpu_fit_seconds(ns, lh, X, y)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_fit_seconds(ns, lh, X, y)
+        _, v = cpu_fit_seconds(ns, lh, X, y)
     el = time.perf_counter() - t0
     scale = (N_FIT / ns) ** 3
     per_fit = el / steps * scale
     val = 1.0 / per_fit
-    sample = ("each step = one compute_likelihood of the oracle port of GPr.py:57-69 at N=%d (first %d points), "
-              "%.3f s/step measured, extrapolated x%.0f (cubic) to N=16384" % (ns, ns, el / steps, scale))
+    if ns == N_FIT:
+        sample = ("MEASURED: each step = one compute_likelihood of the oracle port of GPr.py:57-69 at the full N=16384, "
+                  "%.1f s/step, nlml %.6f" % (el / steps, v))
+    else:
+        sample = ("each step = one compute_likelihood of the oracle port of GPr.py:57-69 at N=%d (first %d points), "
+                  "%.3f s/step measured, extrapolated x%.0f (cubic) to N=16384" % (ns, ns, el / steps, scale))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "fits/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": per_fit * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n": N_FIT, "d": D_FIT},
-            "cpu_baseline": {"value": val, "unit": "fits/s", "cores": blas_threads(), "kind": "port", "sample": sample,
-                             "host_cpus": os.cpu_count()},
+            "cpu_baseline": {"value": val, "unit": "fits/s", "cores": cores, "kind": "port", "sample": sample,
+                             "host_cpus": os.cpu_count(), "extrapolated": ns != N_FIT},
             "e2e": {"value": val, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -276,14 +314,14 @@ def run_ours(args, rank, world, local_rank):
     extra = {}
     if rank == 0 and world == 1 and not args.skip_extras:
         extra = single_gpu_extras(h, X, y, Z, lh)
+    dmma_peak = h.microbench(0)
     if args.sweep:
-        extra["sweep_1024x2048"] = sweep_c5(h, rank, world, dist, torch)
+        extra["sweep_1024x2048"] = sweep_c5(h, rank, world, dist, torch, dmma_peak)
 
     if rank == 0:
         fits_per_s = world * steps / (ms_max * 1e-3)
         flops_chol = N_FIT ** 3 / 3.0
         chol_tflops = flops_chol / (stage["factor_ms"] * 1e-3) / 1e12
-        dmma_peak = h.microbench(0)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -305,13 +343,25 @@ def run_ours(args, rank, world, local_rank):
             "stage_ms": stage,
             "roofline": {"bound": "tensor", "achieved": chol_tflops, "peak": dmma_peak, "unit": "TFLOP/s",
                          "frac": chol_tflops / dmma_peak, "traffic": traffic,
+                         "traffic_source": "profiles/traffic.json: one ncu --set full capture of dmma_gemm_nt_kernel at the "
+                                           "K=512 trailing-update shape (static file, per launch; not measured in this run)",
+                         "frac_vs_cublas": (chol_tflops / extra["cublas_dgemm_8192_tflops"]) if extra.get("cublas_dgemm_8192_tflops") else None,
+                         "frac_vs_nominal_40": chol_tflops / 40.0,
                          "kernel": "dmma_gemm_nt_kernel inside the factorisation stage (N^3/3 flop / CUDA-event stage time, panels included)",
                          "peak_source": "FP64 DMMA.8x8x4 pipe rate measured in this run (gpb_microbench); MEASURED_PEAKS.json has no fp64 entry; nominal 37 TFLOP/s",
                          "peak_cublas_dgemm": extra.get("cublas_dgemm_8192_tflops")},
             "roofline_kbuild": {"bound": "hbm", "achieved": extra.get("kxx_full_GBs"), "peak": hbm_peak, "unit": "GB/s",
                                 "frac": (extra.get("kxx_full_GBs") / hbm_peak) if extra.get("kxx_full_GBs") else None,
                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                                "bytes": 8.0 * N_FIT * N_FIT + 8.0 * N_FIT * D_FIT},
+                                "bytes": 8.0 * N_FIT * N_FIT + 8.0 * N_FIT * D_FIT,
+                                "variant": "full symmetric matrix (compute_Kxx_matrix, GPr.py:99-103)"},
+            "roofline_kbuild_in_path": {"bound": "hbm", "unit": "GB/s", "peak": hbm_peak,
+                                        "bytes": 4.0 * N_FIT * (N_FIT + 1) + 8.0 * N_FIT * D_FIT,
+                                        "ms": stage["kbuild_ms"],
+                                        "achieved": (4.0 * N_FIT * (N_FIT + 1) + 8.0 * N_FIT * D_FIT) / (stage["kbuild_ms"] * 1e-3) / 1e9,
+                                        "frac": (4.0 * N_FIT * (N_FIT + 1) + 8.0 * N_FIT * D_FIT) / (stage["kbuild_ms"] * 1e-3) / 1e9 / hbm_peak,
+                                        "variant": "lower tiles only - what compute_likelihood's timed path builds (stage kbuild_ms also holds "
+                                                   "the point scaling and the y row)"},
             "e2e": {"value": world / (e2e_ms * 1e-3), "unit": "fits/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(X.nbytes + y.nbytes + 8 * (D_FIT + 2)), "d2h_bytes_per_step": 12,
                     "api": "GPr.GaussianProcess.compute_likelihood(hyp), pinned host X/y uploaded every call"},
@@ -378,6 +428,22 @@ def single_gpu_extras(h, X, y, Z, lh):
     out["append_128_points_ms"] = (time.perf_counter() - t0) * 1e3
     h.grow_begin(kh, D_FIT, capacity=1)                       # release the stored factor
     out["other_configs"] = other_configs(h)
+    peak = h.microbench(0)
+    oc = out["other_configs"]
+    c3, c4 = oc["c3_gpc_n8192_d4"], oc["c4_gppref_n4096_p32768"]
+    f3 = (c3["newton_iters"] + 2) * 8192.0 ** 3 / 3.0          # chol(K) jitter check + one chol(B) per Newton step + the final one
+    f4 = 4096.0 ** 3 + c4["iters_reference_semantics"] * 4096.0 ** 3 / 3.0   # potrf + inverse of K, then chol(K^-1 + W) per step
+    fp = N_FIT ** 3 / 3.0 + float(N_FIT) ** 2 * M_TEST          # factor + the TRSM of the predictive variance
+    out["roofline_configs"] = {
+        "peak_tflops": peak, "bound": "tensor",
+        "c3_gpc": {"flops": f3, "ms": c3["ms"], "achieved": f3 / (c3["ms"] * 1e-3) / 1e12, "frac": f3 / (c3["ms"] * 1e-3) / 1e12 / peak},
+        "c4_gppref": {"flops": f4, "ms": c4["ms"], "achieved": f4 / (c4["ms"] * 1e-3) / 1e12, "frac": f4 / (c4["ms"] * 1e-3) / 1e12 / peak},
+        "c2_fit_predict": {"flops": fp, "ms": out["fit_predict_ms"], "achieved": fp / (out["fit_predict_ms"] * 1e-3) / 1e12,
+                           "frac": fp / (out["fit_predict_ms"] * 1e-3) / 1e12 / peak},
+        "c2_fit_grad": {"flops": float(N_FIT) ** 3, "ms": out["fit_grad_ms"], "achieved": out["fit_grad_tflops"],
+                        "frac": out["fit_grad_tflops"] / peak},
+        "note": "algorithmic flops (SURVEY 8d) over the wall time of one public call, host setup included",
+    }
     return out
 
 
@@ -404,33 +470,38 @@ def other_configs(h):
     return res
 
 
-def sweep_c5(h, rank, world, dist, torch):
-    """BASELINE config 5: 1024 independent N=2048 problems, contiguous slices per rank (strong scaling)."""
+def sweep_c5(h, rank, world, dist, torch, dmma_peak=None):
+    """BASELINE config 5 through the product API: gptest_b200.sweep.sweep_nlml shards the 1024 hyper-parameter vectors
+    over the ranks (contiguous slices), every rank uploads (X, y), evaluates its slice with the batched kernels and the
+    results are all-gathered over NCCL - all of it INSIDE the timed region (strong scaling)."""
+    from gptest_b200 import sweep
     X, Y, lhs = make_c5()
     B = len(lhs)
-    lo, hi = rank * B // world, (rank + 1) * B // world
-    kh = np.array([khyp_of(l) for l in lhs[lo:hi]])
-    h.set_train(X, Y)
-    h.gpr_nlml_batched(kh)          # untimed warm-up pass with the same shapes (work space is allocated here)
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    vals, info = h.gpr_nlml_batched(kh)
-    e1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
-    v = torch.from_numpy(vals).cuda()
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        allv = [torch.empty_like(v) for _ in range(world)]
-        dist.all_gather(allv, v)
-        v = torch.cat(allv)
-    ms = t.item()
-    return {"problems": B, "n": 2048, "ms": ms, "fits_per_s": B / (ms * 1e-3),
-            "chol_tflops": B * 2048 ** 3 / 3.0 / (ms * 1e-3) / 1e12, "scaling": "strong",
-            "nlml_checksum": float(v.sum().item()), "failed": int((info != 0).sum())}
+    sweep.sweep_nlml(X, Y, lhs)        # untimed warm-up with the same shapes (work space, NCCL buffers)
+    best, vals = None, None
+    for rep in range(2):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        vals = sweep.sweep_nlml(X, Y, lhs)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        best = ms if best is None else min(best, ms)
+    tf = B * 2048 ** 3 / 3.0 / (best * 1e-3) / 1e12
+    out = {"problems": B, "n": 2048, "ms": best, "fits_per_s": B / (best * 1e-3), "chol_tflops": tf, "scaling": "strong",
+           "api": "gptest_b200.sweep.sweep_nlml (default CUDA evaluator); H2D of (X, y), the batched fits of this rank's slice "
+                  "and the NCCL all-gather of the scalar likelihoods are inside the timed region; best of 2",
+           "nlml_checksum": float(np.where(np.isfinite(vals), vals, 0.0).sum()), "failed": int((~np.isfinite(vals)).sum())}
+    if dmma_peak:
+        out["roofline"] = {"bound": "tensor", "achieved": tf, "peak": dmma_peak, "unit": "TFLOP/s", "frac": tf / dmma_peak,
+                           "flops": "1024 x N^3/3, N = 2048"}
+    return out
 
 
 def main():
@@ -442,6 +513,7 @@ def main():
     ap.add_argument("--sweep", action="store_true", default=True, help="also time the 1024 x N=2048 sweep (config 5)")
     ap.add_argument("--no-sweep", dest="sweep", action="store_false")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--ref-full", action="store_true", help="reference arm at the real N=16384 (minutes per step)")
     ap.add_argument("--skip-extras", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -12,7 +12,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libgpb200.so')
+LIB_PATH = os.environ.get('GPB200_LIB') or os.path.join(_HERE, 'libgpb200.so')     # GPB200_LIB: A/B of two builds (tools/)
 CSRC = os.path.join(_HERE, 'csrc')
 
 _lib = None

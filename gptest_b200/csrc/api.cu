@@ -20,6 +20,15 @@ cudaEvent_t gpb_handle::next_event() {
   return e;
 }
 
+void gpb_handle::prepare_capture() {
+  if (ev_pool.empty()) { next_event(); ev_next = 0; }
+  while (static_cast<int>(su.size()) < dag_streams) {
+    cudaStream_t st;
+    GPB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    su.push_back(st);
+  }
+}
+
 double* gpb_handle::pinned(size_t bytes) {
   if (bytes > h_pinned_bytes) {
     if (h_pinned) cudaFreeHost(h_pinned);
@@ -232,6 +241,8 @@ int gpb_set_option(gpb_handle* h, const char* name, int64_t value) {
   else if (!strcmp(name, "batch_chunk")) h->batch_chunk = value;
   else if (!strcmp(name, "small_tile_threshold")) h->small_tile_threshold = value;
   else if (!strcmp(name, "thin_tile_max")) h->thin_tile_max = value;
+  else if (!strcmp(name, "tri_skip")) h->tri_skip = value != 0;
+  else if (!strcmp(name, "fuse_rhs")) h->fuse_rhs = value != 0;
   else if (!strcmp(name, "split_tiles")) h->split_tiles = value != 0;
   else if (!strcmp(name, "persistent_waves")) dmma_gemm_set_persistent(static_cast<int>(value));
   else if (!strcmp(name, "stagger")) dmma_gemm_set_stagger(static_cast<int>(value));
@@ -244,6 +255,7 @@ int gpb_set_option(gpb_handle* h, const char* name, int64_t value) {
   else if (!strcmp(name, "dag_big_tiles")) h->dag_big_tiles = static_cast<int>(value);
   else if (!strcmp(name, "chain_on_panel_stream")) h->chain_on_panel_stream = static_cast<int>(value);
   else if (!strcmp(name, "pdl_max_tiles")) h->pdl_max_tiles = static_cast<int>(value);
+  else if (!strcmp(name, "pdl_tail")) h->pdl_tail = value != 0;
   else if (!strcmp(name, "dag_min_width")) h->dag_min_width = static_cast<int>(value < 1 ? 1 : value);
   else if (!strcmp(name, "nb_switch4")) h->nb_switch4 = static_cast<int>(value);
   else if (!strcmp(name, "nb_switch2")) h->nb_switch2 = static_cast<int>(value);

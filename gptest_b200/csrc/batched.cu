@@ -96,9 +96,16 @@ extern "C" int gpb_gpr_nlml_batched(gpb_handle* h, const double* khyp, int64_t B
       double* zv = rv + static_cast<size_t>(chunk) * np;
       launch_set_y_rows(rv, np, 0, h->y.as<double>(), h->n, np, mean, bc, h->s0);
       h->launches += 3;
-      chol_sweep(h, m, true);
-      launch_trsv_l(m.A, m.ld, m.batch_stride, m.Dinv, m.dinv_bs, np, rv, np, zv, np, bc, h->s0);
-      h->launches += static_cast<int>(np / TILE);
+      if (h->fuse_rhs) {
+        // z = L^-1 r rides on the factorisation: tile k of it is solved right after diagonal tile k, and the panel
+        // TRSM takes its columns out of the rows below while it still holds them (GemmArgs::gemv_*)
+        m.rhs_r = rv; m.rhs_z = zv; m.rhs_bs = np;
+        chol_sweep(h, m, true);
+      } else {
+        chol_sweep(h, m, true);
+        launch_trsv_l(m.A, m.ld, m.batch_stride, m.Dinv, m.dinv_bs, np, rv, np, zv, np, bc, h->s0);
+        h->launches += static_cast<int>(np / TILE);
+      }
       launch_nlml_finish(zv, np, m.diag, m.diag_bs, np, h->n, h->scal.as<double>(), bc, h->s0);
       ++h->launches;
       double* hres = host + cnt;

@@ -150,6 +150,12 @@ struct Sweep {
     a.j0 = k; a.j1 = k + 1;
     a.ka0 = k * TILE; a.kb0 = 0; a.nk = TILE / GEMM_KB; a.b_row0 = 0;
     a.epi = 0;
+    a.b_tri = h->tri_skip;
+    if (factor && m.rhs_r) {
+      a.gemv_z = m.rhs_z + static_cast<int64_t>(k) * TILE;
+      a.gemv_r = m.rhs_r;
+      a.gemv_bs = m.rhs_bs;
+    }
     const int n128 = gemm_region_tiles(a);
     if (n128 <= 0) return;
     if (static_cast<int64_t>(n128) * m.batch <= h->thin_tile_max) {
@@ -180,6 +186,7 @@ struct Sweep {
     a.j0 = c0; a.j1 = c1; a.i_off = 0;
     a.ka0 = ka * TILE; a.kb0 = ka * TILE; a.nk = (kb - ka) * TILE / GEMM_KB; a.b_row0 = 0;
     a.epi = 1;
+    a.sym_lower = (factor && h->tri_skip) ? 1 : 0;
     launch(a, m.mapA, m.mapA, st);
   }
   void panel(int kb, int kend, cudaStream_t st) {
@@ -191,6 +198,12 @@ struct Sweep {
         t.diag = m.diag; t.diag_batch_stride = m.diag_bs; t.info = m.info; t.pdl = pdl;
         launch_tile_potrf_inv(t, m.batch, st);
         ++h->launches;
+        if (m.rhs_r) {
+          // z_k = W_k r_k: every earlier panel TRSM has already taken its columns out of r_k
+          launch_trsv_l(m.A, m.ld, m.batch_stride, m.Dinv, m.dinv_bs, static_cast<int64_t>(k + 1) * TILE, m.rhs_r, m.rhs_bs, m.rhs_z,
+                        m.rhs_bs, m.batch, st, k);
+          ++h->launches;
+        }
       }
       trsm(k, st);
       update(k + 1, kend, k, k + 1, st);
@@ -322,6 +335,8 @@ void chol_sweep(gpb_handle* h, FactorMat& m, const SweepPlan& plan) {
     while (kend < nt) {
       const int nbn = width_at(kend);
       const int nend = kend + nbn < nt ? kend + nbn : nt;
+      // the tail of a big matrix is a small matrix: from here on the chain of small launches is the run time again
+      if (h->pdl_tail && nt - kend <= h->pdl_max_tiles) s.pdl = true;
       GPB_CUDA(cudaStreamWaitEvent(h->s1, er, 0));
       s.update(kend, nend, kb, kend, h->s1);           // columns of the next panel ...
       s.panel(kend, nend, h->s1);                      // ... and the panel itself, back to back

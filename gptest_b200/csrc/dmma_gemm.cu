@@ -49,7 +49,9 @@ __device__ __forceinline__ void decode_tile(const GemmArgs& p, int idx, int& it,
 
 // BM x BN output tile per CTA-tile.  The region is described in BM x BM tiles (square BN >= BM
 // configurations: BM x BN); when BN < BM a region tile is cut into BM/BN column slices.
-template <int BM, int BN, int WM, int WN, int MINB>
+// GEMV: the instantiation carries the fused substitution step (GemmArgs::gemv_*); only the panel-TRSM shapes (BN = 128)
+// have one, so the update kernels - where the time is - stay exactly as they were.
+template <int BM, int BN, int WM, int WN, int MINB, bool GEMV = false>
 __global__ void __launch_bounds__(WM * WN * 32, MINB)
 dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const GemmArgs p) {
@@ -64,6 +66,7 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   constexpr int NSPLIT = (BN < BM) ? BM / BN : 1;
 
   extern __shared__ uint8_t smem_raw[];
+  __shared__ double gemv_red[GEMV ? WN : 1][GEMV ? BM : 1];   // per column group of warps: row sums of the fused substitution step
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * STAGE);
   uint64_t* empty = full + GEMM_STAGES;
@@ -134,8 +137,11 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   }
 
   // ---------------- DMMA consumers ----------------
+  // Warp w runs on scheduler w % 4.  With a triangular B tile the work of a warp grows with its column group wn, so
+  // the second row of warps takes the column groups in reverse order: every scheduler then carries a light and a
+  // heavy warp (WN = 4), instead of one scheduler carrying both warps that need all k slabs.
   const int wm = warp / WN;
-  const int wn = warp % WN;
+  const int wn = (wm & 1) ? WN - 1 - warp % WN : warp % WN;
   const int g = lane >> 2;         // fragment row (A) / column (B)
   const int t = lane & 3;          // fragment k index
   const int th = t >> 1;
@@ -159,8 +165,11 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       jt = jt * NSPLIT + w % NSPLIT;
     }
     const int nk = p.k_from_row ? (p.k_end - it * BM) / GEMM_KB : p.nk;
+    // slabs this warp multiplies (b_tri) and whether its tile is needed at all (sym_lower)
+    const int nk_warp = p.b_tri ? min(nk, ((wn + 1) * BNW + GEMM_KB - 1) / GEMM_KB) : nk;
+    const bool dead = p.sym_lower && (it * BM + wm * BMW + BMW - 1 < jt * BN + wn * BNW);
 
-    if (p.epi == 1) {
+    if (p.epi == 1 && !dead) {
       // pull this warp's piece of C towards L2 while the k loop runs (128-byte lines)
       const double* Cp = p.C + static_cast<int64_t>(batch) * p.c_batch_stride;
       const int64_t rb = static_cast<int64_t>(it) * BM + wm * BMW;
@@ -192,6 +201,7 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       mbar_wait(&full[st], (n_done / GEMM_STAGES) & 1);
       const uint8_t* sa = smem + st * STAGE;
       const uint8_t* sb = sa + SLAB_A;
+      if (s < nk_warp && !dead) {
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         double af[2 * GM], bf[2 * GN];
@@ -210,9 +220,44 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
           for (int nj = 0; nj < 2 * GN; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], af[mi], bf[nj]);
       }
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[st]);
       ++n_done;
+    }
+
+    if (GEMV && p.gemv_r != nullptr) {
+      // r[row] -= X[row][:] . z for the rows of this CTA-tile (BN = 128: the tile spans the whole column block).
+      // Lane partial sums over its own columns, 4 lanes of a row by shuffle, the WN column groups through shared
+      // memory in a fixed order: deterministic.
+      const double* zt = p.gemv_z + static_cast<int64_t>(batch) * p.gemv_bs + wn * BNW;
+      double zl[2 * GN][2];
+#pragma unroll
+      for (int gn = 0; gn < GN; ++gn)
+#pragma unroll
+        for (int pn = 0; pn < 2; ++pn)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) zl[gn * 2 + pn][e] = zt[16 * gn + 4 * t + 2 * e + pn];
+#pragma unroll
+      for (int mi = 0; mi < 2 * GM; ++mi) {
+        double sdot = 0.0;
+#pragma unroll
+        for (int nj = 0; nj < 2 * GN; ++nj) sdot = fma(acc[mi][nj][0], zl[nj][0], fma(acc[mi][nj][1], zl[nj][1], sdot));
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+        if (t == 0) gemv_red[wn][wm * BMW + 16 * (mi >> 1) + 2 * g + (mi & 1)] = sdot;
+      }
+      __syncthreads();
+      if (threadIdx.x < BM) {
+        const int64_t row = static_cast<int64_t>(it) * BM + threadIdx.x;
+        if (row < p.rows_total) {
+          double tot = gemv_red[0][threadIdx.x];
+#pragma unroll
+          for (int w = 1; w < WN; ++w) tot += gemv_red[w][threadIdx.x];
+          p.gemv_r[static_cast<int64_t>(batch) * p.gemv_bs + row] -= tot;
+        }
+      }
+      __syncthreads();
     }
 
     // ---------------- epilogue: each lane owns 4 consecutive columns per (row, column group) -------
@@ -226,7 +271,7 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
       for (int pm = 0; pm < 2; ++pm) {
         const int64_t row = row_base + 16 * gm + 2 * g + pm;
-        if (row < p.rows_total && (p.epi != 2 || acc[0][0][0] == 1.2345e300)) {   // epi 2: measurement only, no stores
+        if (row < p.rows_total && !dead && (p.epi != 2 || acc[0][0][0] == 1.2345e300)) {   // epi 2: measurement only, no stores
           const int mi = gm * 2 + pm;
 #pragma unroll
           for (int gn = 0; gn < GN; ++gn) {
@@ -287,6 +332,14 @@ void dmma_gemm_init() {
                                 smem_bytes(128, 64)));
   GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<32, 128, 2, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 smem_bytes(32, 128)));
+  GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<128, 128, 2, 4, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                smem_bytes(128, 128)));
+  GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<64, 128, 2, 4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                smem_bytes(64, 128)));
+  GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<64, 128, 2, 2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                smem_bytes(64, 128)));
+  GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<32, 128, 2, 4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                smem_bytes(32, 128)));
   GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<32, 64, 2, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 smem_bytes(32, 64)));
   int dev = 0, sms = 0;
@@ -326,7 +379,12 @@ void launch_dmma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmArgs
   // slots the look-ahead panel wants
   const bool small = static_cast<int64_t>(ntiles) * a.nbatch <= 2LL * g_num_sms;
   const bool pdl = g_pdl == 2 || (g_pdl == 1 && small && a.pdl != 0);
-  if (tile == 128) {
+  const bool gemv = a.gemv_r != nullptr;
+  GPB_REQUIRE(!gemv || tile == 128 || tile == 64128 || tile == 32128, "dmma_gemm: the fused substitution step needs a 128-column tile");
+  if (tile == 128 && gemv) {
+    launch_chain(dmma_gemm_nt_kernel<128, 128, 2, 4, 1, true>, grid_for(ntiles, 1), dim3(8 * 32), smem_bytes(128, 128), st, pdl,
+                 mapA, mapB, a);
+  } else if (tile == 128) {
     launch_chain(dmma_gemm_nt_kernel<128, 128, 2, 4, 1>, grid_for(ntiles, 1), dim3(8 * 32), smem_bytes(128, 128), st, pdl,
                  mapA, mapB, a);
   } else if (tile == 12864) {
@@ -336,8 +394,12 @@ void launch_dmma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmArgs
                  mapA, mapB, a);
   } else if (tile == 32128) {
     // 32 x 128, 8 warps of 16 x 32: rows in units of 32, columns in units of 128 (the in-place panel TRSM of a small matrix)
-    launch_chain(dmma_gemm_nt_kernel<32, 128, 2, 4, 2>, grid_for(ntiles, 2), dim3(8 * 32), smem_bytes(32, 128), st, pdl,
-                 mapA, mapB, a);
+    if (gemv)
+      launch_chain(dmma_gemm_nt_kernel<32, 128, 2, 4, 2, true>, grid_for(ntiles, 2), dim3(8 * 32), smem_bytes(32, 128), st, pdl,
+                   mapA, mapB, a);
+    else
+      launch_chain(dmma_gemm_nt_kernel<32, 128, 2, 4, 2>, grid_for(ntiles, 2), dim3(8 * 32), smem_bytes(32, 128), st, pdl,
+                   mapA, mapB, a);
   } else if (tile == 3264) {
     // 32 x 64, 8 warps of 16 x 16: rows in units of 32, columns in units of 64 (single-column update on the critical chain)
     launch_chain(dmma_gemm_nt_kernel<32, 64, 2, 4, 3>, grid_for(ntiles, 3), dim3(8 * 32), smem_bytes(32, 64), st, pdl,
@@ -354,8 +416,15 @@ void launch_dmma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmArgs
                    mapA, mapB, a);
   } else {
     // 64 x 128: rows in units of 64, columns in units of 128 (mapA with 64-row boxes, mapB with 128-row boxes)
-    if (g_fine_warps && static_cast<int64_t>(ntiles) * a.nbatch <= g_num_sms)
+    const bool fine = g_fine_warps && static_cast<int64_t>(ntiles) * a.nbatch <= g_num_sms;
+    if (fine && gemv)
+      launch_chain(dmma_gemm_nt_kernel<64, 128, 2, 4, 2, true>, grid_for(ntiles, 2), dim3(8 * 32), smem_bytes(64, 128), st, pdl,
+                   mapA, mapB, a);
+    else if (fine)
       launch_chain(dmma_gemm_nt_kernel<64, 128, 2, 4, 2>, grid_for(ntiles, 2), dim3(8 * 32), smem_bytes(64, 128), st, pdl,
+                   mapA, mapB, a);
+    else if (gemv)
+      launch_chain(dmma_gemm_nt_kernel<64, 128, 2, 2, 2, true>, grid_for(ntiles, 2), dim3(4 * 32), smem_bytes(64, 128), st, pdl,
                    mapA, mapB, a);
     else
       launch_chain(dmma_gemm_nt_kernel<64, 128, 2, 2, 2>, grid_for(ntiles, 2), dim3(4 * 32), smem_bytes(64, 128), st, pdl,

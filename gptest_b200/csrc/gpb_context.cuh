@@ -39,6 +39,11 @@ struct FactorMat {
   double* diag = nullptr;    // per batch n_pad
   int64_t diag_bs = 0;
   int* info = nullptr;       // per batch
+  // optional right-hand side solved along with the factorisation without an appended row (batched fits): r is
+  // overwritten, z <- L^-1 r; per batch entry n_pad doubles each, stride rhs_bs (see GemmArgs::gemv_*)
+  double* rhs_r = nullptr;
+  double* rhs_z = nullptr;
+  int64_t rhs_bs = 0;
   TileMaps mapA, mapD;
 };
 
@@ -64,6 +69,7 @@ struct gpb_handle {
   int64_t batch_chunk = 0;       // 0 = auto
   int dag_streams = 4;           // > 0: while the block is 4 tiles wide, the trailing update is issued as column chunks
                                  // on this many streams, ordered by events only (see chol.cu); 0 = one launch per step
+  int pdl_tail = 1;              // switch programmatic dependent launch on for the last pdl_max_tiles tile columns of a big sweep
   int pdl_max_tiles = 40;        // look-ahead sweeps of larger matrices launch without programmatic serialisation
   int chain_on_panel_stream = 1; // the update of the next panel's columns runs on the panel stream (chol.cu)
   int dag_min_width = 4;         // narrowest block (tiles) that still uses the chunked schedule
@@ -75,6 +81,9 @@ struct gpb_handle {
                                  // (measured: N=16384 B=4 47.5 vs 50.2 ms/fit, N=4096 B=8 1.08 vs 1.20; 1024x2048 neutral)
   int split_tiles = 1;           // big launches: 1 = 128x64 CTAs, two per SM (finer grain: the look-ahead panel
                                  // kernels get SMs sooner, N=16384: 49.7 vs 52.4 ms); 0 = 128x128, one per SM
+  int fuse_rhs = 1;              // batched fits: forward substitution fused into the panel TRSM (no second pass over L)
+  int tri_skip = 1;              // skip the zero half of the inverted diagonal tile in the panel TRSM and the warp tiles above
+                                 // the diagonal in the symmetric updates (same results, fewer DMMAs)
   int64_t thin_tile_max = 74;    // panel TRSM / single-column update launches with at most this many 128-tiles use 32-row CTA-tiles
   int64_t small_tile_threshold = 2400;  // launches with fewer 128-tiles than this use 64-tiles (tuned: r01_tune_potrf.json)
 
@@ -89,6 +98,8 @@ struct gpb_handle {
   gpb::DevBuf XsT, sq, ZsT, zsq, Zd;
   gpb::DevBuf A, Dinv, diag, info, scal, outv;
   gpb::DevBuf aux0, aux1, aux2;  // stage-specific (gradient / Laplace) scratch
+  gpb::DevBuf trace;             // Laplace loops: (f_error, objective) per iteration, written on the device
+  bool capturing = false;        // a Newton iteration is being captured into a graph: no allocation, no host sync
   double* h_pinned = nullptr;    // pinned staging for small H2D/D2H
   size_t h_pinned_bytes = 0;
 
@@ -111,6 +122,7 @@ struct gpb_handle {
   gpb::GrowState* grow = nullptr;     // gpb_gpr_grow_* state (own buffers: other calls do not disturb it)
 
   cudaEvent_t next_event();
+  void prepare_capture();        // creates everything a sweep may create lazily (event pool, update streams)
   double* pinned(size_t bytes);
 };
 

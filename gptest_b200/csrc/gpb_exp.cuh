@@ -35,10 +35,11 @@ __device__ __forceinline__ void exp_table_to_smem(double* tab) {
   if (threadIdx.x < 64) tab[threadIdx.x] = EXP2_64[threadIdx.x];
 }
 
-// exp(x) for x <= 700; tab = the 64-entry table in shared memory.  Results in the subnormal range come out as
-// s * 2^-1022 (tiny but not flushed: an absolute error below 4.5e-308); below x = -745.2, where numpy's exp
-// returns exactly 0, so does this - the select also covers |x| > 2.3e7 (a scaled distance above ~6800: short
-// length scales, line-search excursions), where k no longer fits the low word and the scale would be garbage.
+// exp(x) for x <= 700; tab = the 64-entry table in shared memory.  Below x = -708 (results under DBL_MIN, where
+// numpy's exp returns subnormals and, from -745.13 on, exactly 0) the result is flushed to 0: an absolute error
+// below 3.4e-308, and exact zeros wherever the reference has them.  The select also covers |x| > 2.3e7 (a scaled
+// distance above ~6800: short length scales, line-search excursions), where k no longer fits the low word and the
+// scale would be garbage.
 __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab) {
   const double kd0 = fma(x, 0x1.71547652b82fep+6, 6755399441055744.0);   // 64/ln2, 2^52 + 2^51: rint in the low word
   const int k = __double2loint(kd0);
@@ -53,7 +54,7 @@ __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ t
   const double s = fma(t, r * p, t);                                     // T * (1 + r p(r)), one rounding
   const int m = max(k >> 6, -1022);
   const double v = s * __hiloint2double((m + 1023) << 20, 0);            // exact scaling by 2^m
-  return x < -745.2 ? 0.0 : v;
+  return x < -708.0 ? 0.0 : v;
 }
 
 // Radial part of the stationary covariance functions, from x = -r^2/2 (r = scaled distance):

@@ -30,6 +30,16 @@ struct GemmArgs {
   long long stagger_clk;    // > 0: delay (SM clocks) of the second resident CTA per SM in the first wave
   int pdl;                  // launch with programmatic stream serialisation if the launch is small (see gpb_common.cuh)
   int no_stagger;           // chunked schedule: CTAs of several launches share the SMs and dephase by themselves
+  int b_tri;                // the B tile is lower triangular (an inverted diagonal tile, the panel TRSM): a warp skips the
+                            // k slabs right of its last output column (they multiply zeros)
+  // Forward substitution riding on the panel TRSM (batched fits, batched.cu): with z = the solved tile z_k of the
+  // right-hand side, the CTA that has produced X = rows of L[., tile k] applies  r[row] -= X[row][:] . z  to its rows
+  // (it owns all 128 columns of them), so L is never read again for the solve.  Null: off.
+  const double* gemv_z;     // per batch entry: 128 doubles (z_k)
+  double* gemv_r;           // per batch entry: the running right-hand side, indexed by global row
+  int64_t gemv_bs;          // elements between batch entries of z / r
+  int sym_lower;            // symmetric update of a factorisation: only the lower triangle of C is ever read, so warp
+                            // tiles that lie strictly above the diagonal are neither computed nor stored
 };
 int gemm_region_tiles(const GemmArgs& a);       // host: number of tiles of the region
 // one tensor map per tile edge: the TMA box height is part of the map

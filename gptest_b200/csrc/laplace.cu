@@ -312,13 +312,43 @@ __global__ void pref_row_kernel(int64_t n, const PrefGraphDev gr, const double* 
   if (g_out) g_out[i] = g;
 }
 
+// ---------------------------------------------------------------------------------------
+// The Newton loops run on the device (GPpref.py:140-155 tests convergence on the host and prints once per
+// iteration).  One iteration is captured into the body of a CUDA-graph WHILE node; the last kernel of the
+// iteration (the finish kernel, thread 0) appends (f_error, objective) to a device trace, counts the iteration,
+// looks at the factorisation's info word and decides whether the loop goes on: cudaGraphSetConditional.  The
+// host launches the graph once and reads counter, status and trace once when it is done - nothing between
+// iterations crosses PCIe and the stream never drains.
+// ---------------------------------------------------------------------------------------
+struct LoopCtl {
+  int it;          // iterations completed
+  int status;      // 0 running / converged, 2: the factorisation inside an iteration failed (pivot holds info)
+  int pivot;
+  int max_iter;
+  double delta_f;
+};
+__device__ __forceinline__ void loop_step(LoopCtl* ctl, double* trace, const int* info, cudaGraphConditionalHandle hc,
+                                          double f_error, double objective) {
+  const int it = ctl->it;
+  trace[2 * it] = f_error;
+  trace[2 * it + 1] = objective;
+  ctl->it = it + 1;
+  const int piv = *info;
+  if (piv != 0) { ctl->status = 2; ctl->pivot = piv; }
+  // GPpref.py:140: while f_error > delta_f (a NaN error ends the loop, as it does on the host)
+  const bool go = piv == 0 && (f_error > ctl->delta_f) && (it + 1 < ctl->max_iter);
+  cudaGraphSetConditional(hc, go ? 1u : 0u);
+}
+
 // lml = sum log Phi(z(f_new)) - 0.5 f_new' iK f_new - 0.5 logdetK - n/2 log(2 pi)   (GPpref.py:90-94)
 // f_error = max |f_new - f| (GPpref.py:151-152); then f <- f_new (GPpref.py:155)
 __global__ void __launch_bounds__(1024) pref_finish_kernel(const int64_t* __restrict__ uvi, const double* __restrict__ y,
                                                            int64_t P, int64_t n, double isqrt2sig,
                                                            const double* __restrict__ f_new, double* __restrict__ f,
                                                            const double* __restrict__ t, const double* __restrict__ logdet,
-                                                           double* __restrict__ out2) {
+                                                           double* __restrict__ out2, LoopCtl* ctl = nullptr,
+                                                           double* trace = nullptr, const int* info = nullptr,
+                                                           cudaGraphConditionalHandle hc = 0) {
   __shared__ double sh[1024];
   double s = 0.0;
   for (int64_t k = threadIdx.x; k < P; k += 1024) {
@@ -335,8 +365,10 @@ __global__ void __launch_bounds__(1024) pref_finish_kernel(const int64_t* __rest
   const double qs = cta_sum<1024>(q, sh);
   const double m = cta_max<1024>(mx, sh);
   if (threadIdx.x == 0) {
+    const double lml = slog - 0.5 * qs - 0.5 * logdet[0] - 0.5 * static_cast<double>(n) * LOG_2PI;
     out2[0] = m;
-    out2[1] = slog - 0.5 * qs - 0.5 * logdet[0] - 0.5 * static_cast<double>(n) * LOG_2PI;
+    out2[1] = lml;
+    if (ctl) loop_step(ctl, trace, info, hc, m, lml);
   }
 }
 
@@ -467,7 +499,8 @@ __global__ void gpc_a_kernel(double* __restrict__ a, const double* __restrict__ 
 // out2 = (max|f_new - f|, -0.5 a'f_new + sum log p(y|f_new)); f <- f_new
 __global__ void __launch_bounds__(1024) gpc_finish_kernel(int link, const double* __restrict__ y, int64_t n,
                                                           const double* __restrict__ a, const double* __restrict__ f_new,
-                                                          double* __restrict__ f, double* __restrict__ out2) {
+                                                          double* __restrict__ f, double* __restrict__ out2, LoopCtl* ctl,
+                                                          double* trace, const int* info, cudaGraphConditionalHandle hc) {
   __shared__ double sh[1024];
   double q = 0.0, mx = 0.0, sl = 0.0;
   for (int64_t i = threadIdx.x; i < n; i += 1024) {
@@ -481,7 +514,11 @@ __global__ void __launch_bounds__(1024) gpc_finish_kernel(int link, const double
   const double qs = cta_sum<1024>(q, sh);
   const double ls = cta_sum<1024>(sl, sh);
   const double m = cta_max<1024>(mx, sh);
-  if (threadIdx.x == 0) { out2[0] = m; out2[1] = -0.5 * qs + ls; }
+  if (threadIdx.x == 0) {
+    out2[0] = m;
+    out2[1] = -0.5 * qs + ls;
+    if (ctl) loop_step(ctl, trace, info, hc, m, -0.5 * qs + ls);
+  }
 }
 // rows[i][j] *= s[j]
 __global__ void scale_cols_kernel(double* __restrict__ rows, int64_t ld, int64_t ncols, const double* __restrict__ s) {
@@ -601,6 +638,91 @@ PrefState* pref_state_checked(gpb_handle* h) {
               "no preference Laplace state on this handle: call gpb_pref_laplace first (any other call that uses "
               "the work space invalidates it)");
   return ps;
+}
+
+// Runs `iteration(handle)` - which enqueues ONE Newton iteration on h->s0 (side streams joined by events, as
+// chol_sweep does) and ends with a finish kernel calling loop_step - as the body of a WHILE node until the device
+// says stop.  Returns the number of kernel launches of one iteration.  ctl / trace: device; result read by the caller.
+struct LoopResult { int it, status, pivot; int64_t launches_per_iteration; };
+template <class F>
+LoopResult run_device_loop_once(gpb_handle* h, LoopCtl* ctl_dev, double* trace_dev, double* trace_host, double delta_f,
+                                int max_iter, F& iteration) {
+  LoopCtl init{0, 0, 0, max_iter, delta_f};
+  LoopCtl* hc_host = reinterpret_cast<LoopCtl*>(h->pinned(sizeof(LoopCtl) + 64));
+  *hc_host = init;
+  GPB_CUDA(cudaMemcpyAsync(ctl_dev, hc_host, sizeof(LoopCtl), cudaMemcpyHostToDevice, h->s0));
+  h->prepare_capture();
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  LoopResult res{0, 0, 0, 0};
+  const int64_t l0 = h->launches;
+  try {
+    GPB_CUDA(cudaGraphCreate(&graph, 0));
+    cudaGraphConditionalHandle cond;
+    GPB_CUDA(cudaGraphConditionalHandleCreate(&cond, graph, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams np{};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = cond;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t node;
+    GPB_CUDA(cudaGraphAddNode(&node, graph, nullptr, 0, &np));
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    GPB_CUDA(cudaStreamBeginCaptureToGraph(h->s0, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    h->capturing = true;
+    try {
+      iteration(cond);
+    } catch (...) {
+      h->capturing = false;
+      cudaGraph_t dummy = nullptr;
+      cudaStreamEndCapture(h->s0, &dummy);
+      throw;
+    }
+    h->capturing = false;
+    GPB_CUDA(cudaStreamEndCapture(h->s0, nullptr));
+    res.launches_per_iteration = h->launches - l0;
+    h->launches = l0;
+    GPB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    GPB_CUDA(cudaGraphLaunch(exec, h->s0));
+    GPB_CUDA(cudaMemcpyAsync(hc_host, ctl_dev, sizeof(LoopCtl), cudaMemcpyDeviceToHost, h->s0));
+    GPB_CUDA(cudaStreamSynchronize(h->s0));
+    res.it = hc_host->it; res.status = hc_host->status; res.pivot = hc_host->pivot;
+    if (res.it > 0 && trace_host) {
+      GPB_CUDA(cudaMemcpyAsync(trace_host, trace_dev, static_cast<size_t>(res.it) * 16, cudaMemcpyDeviceToHost, h->s0));
+      GPB_CUDA(cudaStreamSynchronize(h->s0));
+    }
+    h->launches += res.launches_per_iteration * res.it;
+  } catch (...) {
+    h->launches = l0;
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    throw;
+  }
+  cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(graph);
+  return res;
+}
+template <class F>
+LoopResult run_device_loop(gpb_handle* h, LoopCtl* ctl_dev, double* trace_dev, double* trace_host, double delta_f, int max_iter,
+                           F&& iteration) {
+  try {
+    return run_device_loop_once(h, ctl_dev, trace_dev, trace_host, delta_f, max_iter, iteration);
+  } catch (const Error&) {
+    // Programmatic dependent launches are the one construct of an iteration a graph body may refuse (no kernel has
+    // run yet: capture or instantiation failed).  Same graph, plain dependencies.
+    if (g_pdl == 0) throw;
+    cudaGetLastError();
+    const int saved = g_pdl;
+    g_pdl = 0;
+    try {
+      LoopResult r = run_device_loop_once(h, ctl_dev, trace_dev, trace_host, delta_f, max_iter, iteration);
+      g_pdl = saved;
+      return r;
+    } catch (...) {
+      g_pdl = saved;
+      throw;
+    }
+  }
 }
 
 }  // namespace
@@ -740,10 +862,13 @@ int gpb_pref_laplace(gpb_handle* h, const int64_t* uvi, const double* y, int64_t
   FactorMat g = m;
   g.rows_total = np + 1;
   double* brow = g.A + np * g.ld;
-  double* host = h->pinned(64);
-  int it = 0;
-  double last_lml = 0.0;
-  for (; it < max_iter;) {
+  h->trace.ensure(static_cast<size_t>(max_iter) * 16);
+  double* trace_dev = h->trace.as<double>();
+  LoopCtl* ctl = reinterpret_cast<LoopCtl*>(sc + 16);
+  std::vector<double> trace_local;
+  if (!trace) trace_local.resize(static_cast<size_t>(max_iter) * 2);
+  double* trace_host = trace ? trace : trace_local.data();
+  const LoopResult lr = run_device_loop(h, ctl, trace_dev, trace_host, delta_f, max_iter, [&](cudaGraphConditionalHandle cond) {
     pref_pair_kernel<<<static_cast<unsigned>((P + 255) / 256), 256, 0, h->s0>>>(pd.uvi, pd.y, P, f, isq, i2v, pd.dk, pd.wk);
     scale_copy_lower_kernel<<<static_cast<unsigned>(np), 256, 0, h->s0>>>(iK, np, g.A, g.ld, nullptr, 0.0);
     GPB_CUDA(cudaMemsetAsync(brow, 0, np * 8, h->s0));
@@ -755,19 +880,14 @@ int gpb_pref_laplace(gpb_handle* h, const int64_t* uvi, const double* y, int64_t
     chol_sweep(h, g, true);                                  // G = L L^T, appended row <- L^-1 (W f + grad)
     trsv_lt(h, g, brow, f_new);                              // f_new = G^-1 (W f + grad)   (GPpref.py:143)
     launch_row_dot(iK, np, 0, f_new, 0, np, np, 0, t, 0, 1, h->s0);
-    pref_finish_kernel<<<1, 1024, 0, h->s0>>>(pd.uvi, pd.y, P, n, isq, f_new, f, t, sc, sc + 2);
+    pref_finish_kernel<<<1, 1024, 0, h->s0>>>(pd.uvi, pd.y, P, n, isq, f_new, f, t, sc, sc + 2, ctl, trace_dev, g.info, cond);
     GPB_CUDA(cudaGetLastError());
     h->launches += 2;
-    GPB_CUDA(cudaMemcpyAsync(host, sc + 2, 16, cudaMemcpyDeviceToHost, h->s0));
-    GPB_CUDA(cudaMemcpyAsync(host + 2, g.info, 4, cudaMemcpyDeviceToHost, h->s0));
-    GPB_CUDA(cudaStreamSynchronize(h->s0));
-    const int ginfo = *reinterpret_cast<int*>(host + 2);
-    if (ginfo) { if (info) *info = ginfo; throw Error{"K^-1 + W is not positive definite"}; }
-    if (trace) { trace[2 * it] = host[0]; trace[2 * it + 1] = host[1]; }
-    last_lml = host[1];
-    ++it;
-    if (!(host[0] > delta_f)) break;                         // GPpref.py:140
-  }
+  });
+  const int it = lr.it;
+  if (lr.status == 2) { if (info) *info = lr.pivot; throw Error{"K^-1 + W is not positive definite"}; }
+  const double last_lml = it > 0 ? trace_host[2 * (it - 1) + 1] : 0.0;
+  double* host = h->pinned(64);
   GPB_CUDA(cudaEventRecord(h->tev[2], h->s0));
   GPB_CUDA(cudaMemcpyAsync(f_inout, f, n * 8, cudaMemcpyDeviceToHost, h->s0));
   GPB_CUDA(cudaStreamSynchronize(h->s0));
@@ -831,11 +951,14 @@ int gpb_gpc_laplace(gpb_handle* h, const double* y, const double* khyp, int32_t 
   FactorMat g = m;
   g.rows_total = np + 1;
   double* rrow = g.A + np * g.ld;
-  double* host = h->pinned(64);
   const unsigned vb = static_cast<unsigned>((np + 255) / 256);
-  int it = 0;
-  double last_obj = 0.0;
-  for (; it < max_iter;) {
+  h->trace.ensure(static_cast<size_t>(max_iter) * 16);
+  double* trace_dev = h->trace.as<double>();
+  LoopCtl* ctl = reinterpret_cast<LoopCtl*>(sc + 16);
+  std::vector<double> trace_local;
+  if (!trace) trace_local.resize(static_cast<size_t>(max_iter) * 2);
+  double* trace_host = trace ? trace : trace_local.data();
+  const LoopResult lr = run_device_loop(h, ctl, trace_dev, trace_host, delta_f, max_iter, [&](cudaGraphConditionalHandle cond) {
     gpc_terms_kernel<<<vb, 256, 0, h->s0>>>(link, yd, f, n, np, sW, b, nullptr);                 // Alg 3.1 lines 4, 6
     scale_copy_lower_kernel<<<static_cast<unsigned>(np), 256, 0, h->s0>>>(K, np, g.A, g.ld, sW, 1.0);   // B = I + sW K sW
     launch_row_dot(K, np, 0, b, 0, np, np, 0, tv, 0, 1, h->s0);                                  // K b
@@ -846,19 +969,14 @@ int gpb_gpc_laplace(gpb_handle* h, const double* y, const double* khyp, int32_t 
     trsv_lt(h, g, rrow, tv);                                                                     // L^T \ ( L \ (sW K b) )
     gpc_a_kernel<<<vb, 256, 0, h->s0>>>(a, b, sW, tv, np);                                       // line 7
     launch_row_dot(K, np, 0, a, 0, np, np, 0, f_new, 0, 1, h->s0);                               // line 8: f = K a
-    gpc_finish_kernel<<<1, 1024, 0, h->s0>>>(link, yd, n, a, f_new, f, sc + 2);
+    gpc_finish_kernel<<<1, 1024, 0, h->s0>>>(link, yd, n, a, f_new, f, sc + 2, ctl, trace_dev, g.info, cond);
     GPB_CUDA(cudaGetLastError());
     h->launches += 7;
-    GPB_CUDA(cudaMemcpyAsync(host, sc + 2, 16, cudaMemcpyDeviceToHost, h->s0));
-    GPB_CUDA(cudaMemcpyAsync(host + 2, g.info, 4, cudaMemcpyDeviceToHost, h->s0));
-    GPB_CUDA(cudaStreamSynchronize(h->s0));
-    const int ginfo = *reinterpret_cast<int*>(host + 2);
-    if (ginfo) { if (info) *info = ginfo; throw Error{"I + sW K sW is not positive definite"}; }
-    if (trace) { trace[2 * it] = host[0]; trace[2 * it + 1] = host[1]; }
-    last_obj = host[1];
-    ++it;
-    if (!(host[0] > delta_f)) break;
-  }
+  });
+  const int it = lr.it;
+  if (lr.status == 2) { if (info) *info = lr.pivot; throw Error{"I + sW K sW is not positive definite"}; }
+  const double last_obj = it > 0 ? trace_host[2 * (it - 1) + 1] : 0.0;
+  double* host = h->pinned(64);
   // approximate log marginal likelihood at the returned f (Alg 3.1 line 10): W, L re-evaluated at f
   gpc_terms_kernel<<<vb, 256, 0, h->s0>>>(link, yd, f, n, np, sW, b, gv);
   scale_copy_lower_kernel<<<static_cast<unsigned>(np), 256, 0, h->s0>>>(K, np, g.A, g.ld, sW, 1.0);

@@ -50,8 +50,11 @@ const char* gpb_last_error(gpb_handle* h);            /* h may be NULL: last cre
  * scripts under tools/ use them): "nb_switch8", "nb_switch4", "nb_switch2" (block width 8/4/2 tiles while at least
  * that many tile columns remain), "split_tiles", "small_tile_threshold", "dag_streams", "dag_min_tiles",
  * "dag_min_width", "dag_big_tiles" (chunked multi-stream trailing update), "chain_on_panel_stream", "pdl",
- * "pdl_max_tiles" (programmatic dependent launch), "potrf_variant", "fine_warps", "persistent_waves", "stagger"
- * (see gpb_context.cuh).  "pdl", "potrf_variant", "fine_warps", "persistent_waves" and "stagger" are process-wide, the rest per
+ * "pdl_max_tiles", "pdl_tail" (programmatic dependent launch), "potrf_variant" (3: diagonal tile blocked inside the CTA,
+ * the default; 2: the register-resident sweep of round 1), "potrf_refine", "thin_tile_max" (32-row CTA-tiles on the panel
+ * chain), "tri_skip" (zero / unused halves skipped in the panel TRSM and the symmetric updates), "fuse_rhs" (batched
+ * fits: forward substitution inside the panel TRSM), "fine_warps", "persistent_waves", "stagger" (see gpb_context.cuh).
+ * "pdl", "potrf_variant", "potrf_refine", "fine_warps", "persistent_waves" and "stagger" are process-wide, the rest per
  * handle.  Returns <0 if unknown. */
 int gpb_set_option(gpb_handle* h, const char* name, int64_t value);
 /* stage times (ms) of the last GPr/potrf call measured with CUDA events on the handle's

@@ -274,3 +274,26 @@ def test_alternative_kernel_paths_agree_with_the_default(handle, opt, val):
         handle.set_option(opt, {'potrf_variant': 3, 'split_tiles': 1, 'lookahead': 1}[opt])
     assert np.abs(L0 - np.linalg.cholesky(A)).max() < 1e-12
     assert np.abs(L1 - L0).max() < 1e-12
+
+
+@pytest.mark.parametrize('bad', [0, 5, 31, 32, 40, 100, 127, 128, 200, 383])
+def test_first_failing_pivot_is_reported_like_lapack(handle, bad):
+    """np.linalg.cholesky (GPr.py:62) raises on a non-positive pivot; the C ABI reports LAPACK's info = index of the
+    first failing leading minor, wherever it falls inside the blocked diagonal-tile kernel (32-blocks, 8-column panels)."""
+    n = 384
+    rng = np.random.default_rng(bad)
+    M = rng.standard_normal((n, n))
+    A = M @ M.T / n + np.eye(n)
+    # make the leading minor of order bad+1 singular-negative: subtract enough from the diagonal entry
+    L = np.linalg.cholesky(A)
+    A[bad, bad] -= 1.5 * L[bad, bad] ** 2
+    with pytest.raises(np.linalg.LinAlgError) as e:
+        handle.potrf(A)
+    assert 'leading minor %d)' % (bad + 1) in str(e.value)
+    handle.set_option('potrf_variant', 2)
+    try:
+        with pytest.raises(np.linalg.LinAlgError) as e2:
+            handle.potrf(A)
+    finally:
+        handle.set_option('potrf_variant', 3)
+    assert 'leading minor %d)' % (bad + 1) in str(e2.value)
