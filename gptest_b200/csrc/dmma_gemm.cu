@@ -139,9 +139,10 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   // ---------------- DMMA consumers ----------------
   // Warp w runs on scheduler w % 4.  With a triangular B tile the work of a warp grows with its column group wn, so
   // the second row of warps takes the column groups in reverse order: every scheduler then carries a light and a
-  // heavy warp (WN = 4), instead of one scheduler carrying both warps that need all k slabs.
+  // heavy warp (WN = 4), instead of one scheduler carrying both warps that need all k slabs.  Only then: in the
+  // plain update kernels the reversed order measured 1.3 % slower at N = 16384 (profiles/r02_ab_kernel_variants.txt).
   const int wm = warp / WN;
-  const int wn = (wm & 1) ? WN - 1 - warp % WN : warp % WN;
+  const int wn = (p.b_tri && (wm & 1)) ? WN - 1 - warp % WN : warp % WN;
   const int g = lane >> 2;         // fragment row (A) / column (B)
   const int t = lane & 3;          // fragment k index
   const int th = t >> 1;
@@ -189,7 +190,11 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
       for (int j = 0; j < 2 * GN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    for (int s = 0; s < nk; ++s) {
+    // The math loop is kept free of the skip logic (a predicate around the DMMA block cost 3 % at N = 16384): a warp
+    // multiplies its first n_math slabs, then only keeps the slab ring turning for the rest (it must stay in step with
+    // the ring: wait for the slab, release it; warp 0 also keeps refilling).
+    const int n_math = dead ? 0 : nk_warp;
+    for (int s = 0; s < n_math; ++s) {
       if (producer && n_done >= 1 && iss_tile < total) {
         // refill the slot of the slab this warp has just left, once every warp has released it;
         // the slab issued here may already belong to the next tile
@@ -201,7 +206,6 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       mbar_wait(&full[st], (n_done / GEMM_STAGES) & 1);
       const uint8_t* sa = smem + st * STAGE;
       const uint8_t* sb = sa + SLAB_A;
-      if (s < nk_warp && !dead) {
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         double af[2 * GM], bf[2 * GN];
@@ -220,7 +224,18 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
           for (int nj = 0; nj < 2 * GN; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], af[mi], bf[nj]);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);
+      ++n_done;
+    }
+    for (int s = n_math; s < nk; ++s) {
+      if (producer && n_done >= 1 && iss_tile < total) {
+        mbar_wait(&empty[(n_done - 1) % GEMM_STAGES], ((n_done - 1) / GEMM_STAGES) & 1);
+        issue_next();
       }
+      __syncwarp();
+      const int st = n_done % GEMM_STAGES;
+      mbar_wait(&full[st], (n_done / GEMM_STAGES) & 1);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[st]);
       ++n_done;

@@ -65,11 +65,12 @@ struct gpb_handle {
   int nb_tiles = 0;              // 0 = choose from the remaining matrix size (see chol.cu)
   int nb_switch8 = 96;           // > 0: blocks of 8 tiles (K = 1024) while at least this many tile columns remain
                                  // (N = 16384: 48.15 vs 48.5 ms with the chunked schedule, profiles/r01_dag_ab.json)
-  int nb_switch4 = 64, nb_switch2 = 40;   // remaining tile columns from which the block is 4 / 2 tiles wide
+  int nb_switch4 = 64, nb_switch2 = 24;   // (round 2: 2-tile blocks down to 24 remaining columns - the faster panel chain hides behind K = 256 updates longer)
+    // remaining tile columns from which the block is 4 / 2 tiles wide
   int64_t batch_chunk = 0;       // 0 = auto
   int dag_streams = 4;           // > 0: while the block is 4 tiles wide, the trailing update is issued as column chunks
                                  // on this many streams, ordered by events only (see chol.cu); 0 = one launch per step
-  int pdl_tail = 1;              // switch programmatic dependent launch on for the last pdl_max_tiles tile columns of a big sweep
+  int pdl_tail = 0;              // switch programmatic dependent launch on for the last pdl_max_tiles tile columns of a big sweep
   int pdl_max_tiles = 40;        // look-ahead sweeps of larger matrices launch without programmatic serialisation
   int chain_on_panel_stream = 1; // the update of the next panel's columns runs on the panel stream (chol.cu)
   int dag_min_width = 4;         // narrowest block (tiles) that still uses the chunked schedule
