@@ -222,6 +222,7 @@ int gpb_destroy(gpb_handle* h) {
   cudaDeviceSynchronize();
   if (h->own_s0 && h->s0) cudaStreamDestroy(h->s0);
   if (h->s1) cudaStreamDestroy(h->s1);
+  if (h->s_loop) cudaStreamDestroy(h->s_loop);
   for (auto s : h->su) cudaStreamDestroy(s);
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   for (auto e : h->tev) if (e) cudaEventDestroy(e);
@@ -239,6 +240,7 @@ int gpb_set_option(gpb_handle* h, const char* name, int64_t value) {
   if (!strcmp(name, "lookahead")) h->lookahead = value != 0;
   else if (!strcmp(name, "nb_tiles")) h->nb_tiles = static_cast<int>(value < 0 ? 0 : (value > 8 ? 8 : value));
   else if (!strcmp(name, "batch_chunk")) h->batch_chunk = value;
+  else if (!strcmp(name, "batch_plain_width")) h->batch_plain_width = static_cast<int>(value < 1 ? 1 : (value > 8 ? 8 : value));
   else if (!strcmp(name, "small_tile_threshold")) h->small_tile_threshold = value;
   else if (!strcmp(name, "thin_tile_max")) h->thin_tile_max = value;
   else if (!strcmp(name, "tri_skip")) h->tri_skip = value != 0;

@@ -30,7 +30,8 @@ extern "C" int gpb_gpr_nlml_batched(gpb_handle* h, const double* khyp, int64_t B
     // problems resident at once: bounded by memory (A + Dinv per problem) and by option
     const size_t per_problem = static_cast<size_t>(np) * np * 8 + static_cast<size_t>(np) * TILE * 8 +
                                static_cast<size_t>(d + 2) * np * 8;
-    int64_t chunk = h->batch_chunk > 0 ? h->batch_chunk : 296;     // two full waves of the one-CTA-per-tile panel kernel on 148 SMs
+    int64_t chunk = h->batch_chunk > 0 ? h->batch_chunk : 1024;    // (round 1: 296 = two waves of the 46 us diagonal-tile kernel; with the 26 us
+                                                                   // kernel fewer, longer chunks win: 296 / 512 / 1024 problems 116.0 / 115.3 / 111.0 ms incl. 4-tile blocks, profiles/r02_ab_sweep.txt)
     if (chunk > B) chunk = B;
     if (chunk > 65535) chunk = 65535;
     if (static_cast<size_t>(chunk) * np * np * 8 > h->A.bytes) {

@@ -238,12 +238,13 @@ void chol_sweep(gpb_handle* h, FactorMat& m, const SweepPlan& plan) {
   // narrow ones keep the panel short where it cannot be hidden (measured: profiles/r01_tune_potrf.json).
   // With nb_tiles == 0 the width follows the REMAINING matrix: 4 tiles while the trailing update is long
   // enough to hide a 4-tile panel, then 2, then 1 in the panel-bound tail.
-  // batches of small matrices (fewer than 24 tile columns) are throughput problems: plain order, blocks of 2 tiles
-  // (1024 x N=2048: 124.7 vs 126.1 ms, 256 x N=1024: 5.3 vs 5.6 ms; from N=4096 on the look-ahead schedule wins)
+  // batches of small matrices (fewer than 24 tile columns) are throughput problems: plain order, blocks of 4 tiles
+  // (round 1, 46 us diagonal tile: 2-tile blocks, 1024 x N=2048 124.7 vs 126.1 ms; round 2, 26 us tile: 4-tile blocks
+  // 112.7 vs 114.0 ms; from N=4096 on the look-ahead schedule wins)
   const bool batch_plain = m.batch > 1 && (m.batch > h->la_max_batch || nt < 24);
   auto width_at = [&](int kb) {
     if (h->nb_tiles > 0) return h->nb_tiles;
-    if (batch_plain) return 2;
+    if (batch_plain) return h->batch_plain_width;
     // a small batch of big problems: the trailing update holds batch x the tiles, so the panel hides as it
     // would behind a single matrix sqrt(batch) times larger
     int rem = nt - kb;

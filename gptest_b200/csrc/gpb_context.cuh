@@ -56,6 +56,7 @@ struct gpb_handle {
   cudaStream_t s0 = nullptr;     // the handle's stream (all results are ordered on it)
   bool own_s0 = false;
   cudaStream_t s1 = nullptr;     // high-priority side stream for the look-ahead panel
+  cudaStream_t s_loop = nullptr; // origin stream of the Laplace graph loops when s0 is the (uncapturable) legacy default stream
   std::vector<cudaStream_t> su;  // update streams of the chunked schedule (created on first use)
   std::string err;
   int64_t launches = 0;
@@ -68,6 +69,7 @@ struct gpb_handle {
   int nb_switch4 = 64, nb_switch2 = 24;   // (round 2: 2-tile blocks down to 24 remaining columns - the faster panel chain hides behind K = 256 updates longer)
     // remaining tile columns from which the block is 4 / 2 tiles wide
   int64_t batch_chunk = 0;       // 0 = auto
+  int batch_plain_width = 4;     // outer block width (tiles) of the plain-order sweep of a batch of small matrices
   int dag_streams = 4;           // > 0: while the block is 4 tiles wide, the trailing update is issued as column chunks
                                  // on this many streams, ordered by events only (see chol.cu); 0 = one launch per step
   int pdl_tail = 0;              // switch programmatic dependent launch on for the last pdl_max_tiles tile columns of a big sweep

@@ -17,6 +17,9 @@
 #include <vector>
 
 #include "../../include/gpb200.h"
+#include <chrono>
+#include <cstdlib>
+
 #include "gpb_context.cuh"
 
 using namespace gpb;
@@ -652,6 +655,22 @@ LoopResult run_device_loop_once(gpb_handle* h, LoopCtl* ctl_dev, double* trace_d
   *hc_host = init;
   GPB_CUDA(cudaMemcpyAsync(ctl_dev, hc_host, sizeof(LoopCtl), cudaMemcpyHostToDevice, h->s0));
   h->prepare_capture();
+  // The legacy default stream (what a caller gets from torch.cuda.current_stream() unless it made one) cannot be
+  // captured: the loop then runs on a stream of the handle's own, ordered after the caller's stream by an event and
+  // synchronised before this function returns.
+  struct StreamSwap {
+    gpb_handle* h;
+    cudaStream_t user;
+    bool on;
+    ~StreamSwap() { if (on) h->s0 = user; }
+  } swap{h, h->s0, h->s0 == nullptr || h->s0 == cudaStreamLegacy || h->s0 == cudaStreamPerThread};
+  if (swap.on) {
+    if (!h->s_loop) GPB_CUDA(cudaStreamCreateWithFlags(&h->s_loop, cudaStreamNonBlocking));
+    cudaEvent_t e = h->next_event();
+    GPB_CUDA(cudaEventRecord(e, swap.user));
+    GPB_CUDA(cudaStreamWaitEvent(h->s_loop, e, 0));
+    h->s0 = h->s_loop;
+  }
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   LoopResult res{0, 0, 0, 0};
@@ -668,6 +687,7 @@ LoopResult run_device_loop_once(gpb_handle* h, LoopCtl* ctl_dev, double* trace_d
     cudaGraphNode_t node;
     GPB_CUDA(cudaGraphAddNode(&node, graph, nullptr, 0, &np));
     cudaGraph_t body = np.conditional.phGraph_out[0];
+    const auto t_cap0 = std::chrono::steady_clock::now();
     GPB_CUDA(cudaStreamBeginCaptureToGraph(h->s0, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
     h->capturing = true;
     try {
@@ -682,8 +702,14 @@ LoopResult run_device_loop_once(gpb_handle* h, LoopCtl* ctl_dev, double* trace_d
     GPB_CUDA(cudaStreamEndCapture(h->s0, nullptr));
     res.launches_per_iteration = h->launches - l0;
     h->launches = l0;
+    const auto t_cap1 = std::chrono::steady_clock::now();
     GPB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    const auto t_cap2 = std::chrono::steady_clock::now();
     GPB_CUDA(cudaGraphLaunch(exec, h->s0));
+    if (getenv("GPB_DEBUG_LOOP"))
+      fprintf(stderr, "[gpb] device loop: %lld launches per iteration, capture %.3f ms, instantiate %.3f ms, pdl %d\n",
+              static_cast<long long>(res.launches_per_iteration), std::chrono::duration<double, std::milli>(t_cap1 - t_cap0).count(),
+              std::chrono::duration<double, std::milli>(t_cap2 - t_cap1).count(), g_pdl);
     GPB_CUDA(cudaMemcpyAsync(hc_host, ctl_dev, sizeof(LoopCtl), cudaMemcpyDeviceToHost, h->s0));
     GPB_CUDA(cudaStreamSynchronize(h->s0));
     res.it = hc_host->it; res.status = hc_host->status; res.pivot = hc_host->pivot;
@@ -710,6 +736,7 @@ LoopResult run_device_loop(gpb_handle* h, LoopCtl* ctl_dev, double* trace_dev, d
   } catch (const Error&) {
     // Programmatic dependent launches are the one construct of an iteration a graph body may refuse (no kernel has
     // run yet: capture or instantiation failed).  Same graph, plain dependencies.
+    if (getenv("GPB_DEBUG_LOOP")) fprintf(stderr, "[gpb] device loop: first attempt failed (%s), retrying without PDL\n", h->err.c_str());
     if (g_pdl == 0) throw;
     cudaGetLastError();
     const int saved = g_pdl;

@@ -238,3 +238,26 @@ def test_pref_log_marginal_on_device(handle, n, P):
         lik = GPpref.PrefProbit(sigma)
         got = lik.log_marginal(uvi, y, f, iK, logdetK)
         assert isinstance(got, float) and abs(got - ref) <= 1e-10 * max(1.0, abs(ref))
+
+
+def test_laplace_loops_on_the_callers_default_stream():
+    """A caller may hand the library the legacy default stream (torch.cuda.current_stream() is that one unless the
+    caller made a stream): it cannot be captured into a graph, so the device loop runs on a stream of the handle's own,
+    ordered after the caller's.  Same numbers as on the handle's stream."""
+    from gptest_b200 import _lib
+    h = _lib.Handle(0)
+    try:
+        h.set_stream(0)
+        x, uvi, y, lh = PREF['k3_x'], PREF['k3_uvi'], PREF['k3_y'].astype(float), PREF['k3_loghyp']
+        h.set_train(x)
+        f, lml, iters, trace, jit = h.pref_laplace(uvi, y, pref_khyp(lh, 1), delta_f=1e-5)
+        assert iters == 5 and np.abs(f - PREF['k3_f'][:, 0]).max() < 1e-6
+        assert abs(lml - float(PREF['k3_lml'])) <= 1e-8 * abs(float(PREF['k3_lml']))
+        xc, yc, zc = make_gpc(300, 2, seed=302)
+        lhc = np.log([0.5, 0.5, 1.0])
+        of, olml, st = gpc_oracle.calc_laplace(xc, yc, lhc, return_state=True)
+        h.set_train(xc)
+        fc, lmlc, itc, _, _ = h.gpc_laplace(yc, np.array([0.5, 0.5, 1.0]))
+        assert itc == st['it'] and np.abs(fc - of).max() < 1e-6 and abs(lmlc - olml) <= 1e-8 * abs(olml)
+    finally:
+        h.close()
