@@ -326,6 +326,7 @@ static int g_num_sms = 148;
 static int g_persistent_waves = 0;
 void dmma_gemm_set_persistent(int waves) { g_persistent_waves = waves < 0 ? 0 : waves; }
 int g_pdl = 1;
+int g_capturing = 0;
 void dmma_gemm_set_pdl(int mode) { g_pdl = mode < 0 ? 0 : mode; }
 static int g_fine_warps = 1;
 void dmma_gemm_set_fine_warps(int on) { g_fine_warps = on != 0; }

@@ -110,17 +110,32 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 extern int g_pdl;       // 0: off  1: the small launches of dependent chains (default)  2: every launch (dmma_gemm.cu)
+extern int g_capturing; // != 0 while a Newton iteration is being captured into a graph body (laplace.cu): launches then
+                        // carry their stream's priority as an explicit attribute, so that the look-ahead panel keeps
+                        // its precedence over the trailing update inside the graph
 
 template <class... KArgs, class... Args>
 inline void launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
                          Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (g_capturing) {
+    int prio = 0;
+    if (cudaStreamGetPriority(st, &prio) == cudaSuccess) {
+      at[na].id = cudaLaunchAttributePriority;
+      at[na].val.priority = prio;
+      ++na;
+    }
+  }
   cfg.attrs = at;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = na;
   GPB_CUDA(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
 }
 

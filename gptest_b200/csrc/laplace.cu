@@ -340,34 +340,54 @@ __device__ __forceinline__ void loop_step(LoopCtl* ctl, double* trace, const int
   if (piv != 0) { ctl->status = 2; ctl->pivot = piv; }
   // GPpref.py:140: while f_error > delta_f (a NaN error ends the loop, as it does on the host)
   const bool go = piv == 0 && (f_error > ctl->delta_f) && (it + 1 < ctl->max_iter);
-  cudaGraphSetConditional(hc, go ? 1u : 0u);
+  if (hc) cudaGraphSetConditional(hc, go ? 1u : 0u);
+  else ctl->status = (ctl->status == 2) ? 2 : (go ? 0 : 1);      // diagnostic host-driven mode (GPB_HOST_LOOP): 1 = stop
 }
 
 // lml = sum log Phi(z(f_new)) - 0.5 f_new' iK f_new - 0.5 logdetK - n/2 log(2 pi)   (GPpref.py:90-94)
 // f_error = max |f_new - f| (GPpref.py:151-152); then f <- f_new (GPpref.py:155)
-__global__ void __launch_bounds__(1024) pref_finish_kernel(const int64_t* __restrict__ uvi, const double* __restrict__ y,
-                                                           int64_t P, int64_t n, double isqrt2sig,
-                                                           const double* __restrict__ f_new, double* __restrict__ f,
-                                                           const double* __restrict__ t, const double* __restrict__ logdet,
-                                                           double* __restrict__ out2, LoopCtl* ctl = nullptr,
-                                                           double* trace = nullptr, const int* info = nullptr,
-                                                           cudaGraphConditionalHandle hc = 0) {
-  __shared__ double sh[1024];
+// Two stages: the P log-Phi terms are ~100 FP64 operations each - on ONE SM (round 1) that was 26 us of its FP64
+// pipe per Newton iteration; now PREF_PARTS CTAs reduce their slices into partials, and the one-CTA finish kernel
+// adds the partials in a fixed order (deterministic) and takes the loop decision.
+constexpr int PREF_PARTS = 64;
+__global__ void __launch_bounds__(256) pref_terms_kernel(const int64_t* __restrict__ uvi, const double* __restrict__ y,
+                                                         int64_t P, int64_t n, double isqrt2sig,
+                                                         const double* __restrict__ f_new, const double* __restrict__ f,
+                                                         const double* __restrict__ t, double* __restrict__ part) {
+  __shared__ double sh[256];
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * 256;
   double s = 0.0;
-  for (int64_t k = threadIdx.x; k < P; k += 1024) {
+  for (int64_t k = blockIdx.x * 256 + threadIdx.x; k < P; k += stride) {
     const double z = y[k] * (isqrt2sig * (f_new[uvi[2 * k + 1]] - f_new[uvi[2 * k]]));
     s += log(normcdf(z));
   }
-  const double slog = cta_sum<1024>(s, sh);
+  const double slog = cta_sum<256>(s, sh);
   double q = 0.0, mx = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += 1024) {
+  for (int64_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
     q = fma(f_new[i], t[i], q);
     mx = fmax(mx, fabs(f_new[i] - f[i]));
-    f[i] = f_new[i];
   }
-  const double qs = cta_sum<1024>(q, sh);
-  const double m = cta_max<1024>(mx, sh);
+  const double qs = cta_sum<256>(q, sh);
+  const double m = cta_max<256>(mx, sh);
   if (threadIdx.x == 0) {
+    part[blockIdx.x] = slog;
+    part[PREF_PARTS + blockIdx.x] = qs;
+    part[2 * PREF_PARTS + blockIdx.x] = m;
+  }
+}
+__global__ void __launch_bounds__(256) pref_finish_kernel(int64_t n, const double* __restrict__ f_new, double* __restrict__ f,
+                                                          const double* __restrict__ part, const double* __restrict__ logdet,
+                                                          double* __restrict__ out2, LoopCtl* ctl = nullptr,
+                                                          double* trace = nullptr, const int* info = nullptr,
+                                                          cudaGraphConditionalHandle hc = 0) {
+  for (int64_t i = threadIdx.x; i < n; i += 256) f[i] = f_new[i];
+  if (threadIdx.x == 0) {
+    double slog = 0.0, qs = 0.0, m = 0.0;
+    for (int b = 0; b < PREF_PARTS; ++b) {
+      slog += part[b];
+      qs += part[PREF_PARTS + b];
+      m = fmax(m, part[2 * PREF_PARTS + b]);
+    }
     const double lml = slog - 0.5 * qs - 0.5 * logdet[0] - 0.5 * static_cast<double>(n) * LOG_2PI;
     out2[0] = m;
     out2[1] = lml;
@@ -690,20 +710,24 @@ LoopResult run_device_loop_once(gpb_handle* h, LoopCtl* ctl_dev, double* trace_d
     const auto t_cap0 = std::chrono::steady_clock::now();
     GPB_CUDA(cudaStreamBeginCaptureToGraph(h->s0, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
     h->capturing = true;
+    g_capturing = getenv("GPB_NO_PRIO") ? 0 : 1;
     try {
       iteration(cond);
     } catch (...) {
       h->capturing = false;
+      g_capturing = 0;
       cudaGraph_t dummy = nullptr;
       cudaStreamEndCapture(h->s0, &dummy);
       throw;
     }
     h->capturing = false;
+    g_capturing = 0;
     GPB_CUDA(cudaStreamEndCapture(h->s0, nullptr));
     res.launches_per_iteration = h->launches - l0;
     h->launches = l0;
     const auto t_cap1 = std::chrono::steady_clock::now();
-    GPB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    // per-node priorities (the look-ahead panel stream is a high-priority stream) only count with this flag
+    GPB_CUDA(cudaGraphInstantiate(&exec, graph, getenv("GPB_NO_PRIO") ? 0 : cudaGraphInstantiateFlagUseNodePriority));
     const auto t_cap2 = std::chrono::steady_clock::now();
     GPB_CUDA(cudaGraphLaunch(exec, h->s0));
     if (getenv("GPB_DEBUG_LOOP"))
@@ -728,9 +752,32 @@ LoopResult run_device_loop_once(gpb_handle* h, LoopCtl* ctl_dev, double* trace_d
   cudaGraphDestroy(graph);
   return res;
 }
+// Diagnostic only (GPB_HOST_LOOP=1): the same iteration launched from the host with one synchronisation per iteration,
+// i.e. the structure of the reference (GPpref.py:140-155) and of round 1.  Used to profile the kernels of an iteration
+// with ncu (which does not open the body of a WHILE node) and to measure what the device loop saves.
+template <class F>
+LoopResult run_host_loop(gpb_handle* h, LoopCtl* ctl_dev, double* trace_dev, double* trace_host, double delta_f, int max_iter,
+                         F& iteration) {
+  LoopCtl* hc_host = reinterpret_cast<LoopCtl*>(h->pinned(sizeof(LoopCtl) + 64));
+  *hc_host = LoopCtl{0, 0, 0, max_iter, delta_f};
+  GPB_CUDA(cudaMemcpyAsync(ctl_dev, hc_host, sizeof(LoopCtl), cudaMemcpyHostToDevice, h->s0));
+  LoopResult res{0, 0, 0, 0};
+  for (;;) {
+    const int64_t l0 = h->launches;
+    iteration(0);
+    res.launches_per_iteration = h->launches - l0;
+    GPB_CUDA(cudaMemcpyAsync(hc_host, ctl_dev, sizeof(LoopCtl), cudaMemcpyDeviceToHost, h->s0));
+    GPB_CUDA(cudaStreamSynchronize(h->s0));
+    if (hc_host->status != 0) break;
+  }
+  res.it = hc_host->it; res.status = hc_host->status == 2 ? 2 : 0; res.pivot = hc_host->pivot;
+  if (res.it > 0 && trace_host) GPB_CUDA(cudaMemcpy(trace_host, trace_dev, static_cast<size_t>(res.it) * 16, cudaMemcpyDeviceToHost));
+  return res;
+}
 template <class F>
 LoopResult run_device_loop(gpb_handle* h, LoopCtl* ctl_dev, double* trace_dev, double* trace_host, double delta_f, int max_iter,
                            F&& iteration) {
+  if (getenv("GPB_HOST_LOOP")) return run_host_loop(h, ctl_dev, trace_dev, trace_host, delta_f, max_iter, iteration);
   try {
     return run_device_loop_once(h, ctl_dev, trace_dev, trace_host, delta_f, max_iter, iteration);
   } catch (const Error&) {
@@ -806,7 +853,7 @@ int gpb_pref_log_marginal(gpb_handle* h, const int64_t* uvi, const double* y, in
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
   const size_t o_uvi = take(P * 16), o_y = take(P * 8), o_f = take(ne * 8), o_f2 = take(ne * 8), o_t = take(ne * 8),
-               o_sc = take(64);
+               o_sc = take(64 + 3 * PREF_PARTS * 8);
   h->aux1.ensure(off);
   h->aux2.ensure(static_cast<size_t>(n) * ne * 8);
   char* base = h->aux1.as<char>();
@@ -824,8 +871,9 @@ int gpb_pref_log_marginal(gpb_handle* h, const int64_t* uvi, const double* y, in
   GPB_CUDA(cudaMemcpyAsync(sc, &logdetK, 8, cudaMemcpyHostToDevice, h->s0));
   launch_row_dot(h->aux2.as<double>(), ne, 0, fd, 0, n, ne, 0, td, 0, 1, h->s0);            // t = iK f
   const double isq = 1.0 / (sigma * std::sqrt(2.0));
-  pref_finish_kernel<<<1, 1024, 0, h->s0>>>(reinterpret_cast<const int64_t*>(base + o_uvi),
-                                            reinterpret_cast<const double*>(base + o_y), P, n, isq, fd, f2, td, sc, sc + 2);
+  pref_terms_kernel<<<PREF_PARTS, 256, 0, h->s0>>>(reinterpret_cast<const int64_t*>(base + o_uvi),
+                                                   reinterpret_cast<const double*>(base + o_y), P, n, isq, fd, f2, td, sc + 8);
+  pref_finish_kernel<<<1, 256, 0, h->s0>>>(n, fd, f2, sc + 8, sc, sc + 2);
   GPB_CUDA(cudaGetLastError());
   h->launches += 2;
   double* host = h->pinned(64);
@@ -862,7 +910,7 @@ int gpb_pref_laplace(gpb_handle* h, const int64_t* uvi, const double* y, int64_t
     if (!(eps < 1e8)) { if (info) *info = 1; throw Error{"K + eps*I is not positive definite for any jitter"}; }
   }
   if (jitter) *jitter = eps;
-  h->scal.ensure(256);
+  h->scal.ensure(2048);
   double* sc = h->scal.as<double>();                 // [0] logdetK (= sum log diag L, GPpref.py:131)  [2..3] per-iteration out
   sum_log_kernel<<<1, 512, 0, h->s0>>>(m.diag, np, sc);
   ++h->launches;
@@ -892,6 +940,7 @@ int gpb_pref_laplace(gpb_handle* h, const int64_t* uvi, const double* y, int64_t
   h->trace.ensure(static_cast<size_t>(max_iter) * 16);
   double* trace_dev = h->trace.as<double>();
   LoopCtl* ctl = reinterpret_cast<LoopCtl*>(sc + 16);
+  double* part = sc + 32;                            // 3 x PREF_PARTS partial sums of the finish stage
   std::vector<double> trace_local;
   if (!trace) trace_local.resize(static_cast<size_t>(max_iter) * 2);
   double* trace_host = trace ? trace : trace_local.data();
@@ -907,9 +956,10 @@ int gpb_pref_laplace(gpb_handle* h, const int64_t* uvi, const double* y, int64_t
     chol_sweep(h, g, true);                                  // G = L L^T, appended row <- L^-1 (W f + grad)
     trsv_lt(h, g, brow, f_new);                              // f_new = G^-1 (W f + grad)   (GPpref.py:143)
     launch_row_dot(iK, np, 0, f_new, 0, np, np, 0, t, 0, 1, h->s0);
-    pref_finish_kernel<<<1, 1024, 0, h->s0>>>(pd.uvi, pd.y, P, n, isq, f_new, f, t, sc, sc + 2, ctl, trace_dev, g.info, cond);
+    pref_terms_kernel<<<PREF_PARTS, 256, 0, h->s0>>>(pd.uvi, pd.y, P, n, isq, f_new, f, t, part);
+    pref_finish_kernel<<<1, 256, 0, h->s0>>>(n, f_new, f, part, sc, sc + 2, ctl, trace_dev, g.info, cond);
     GPB_CUDA(cudaGetLastError());
-    h->launches += 2;
+    h->launches += 3;
   });
   const int it = lr.it;
   if (lr.status == 2) { if (info) *info = lr.pivot; throw Error{"K^-1 + W is not positive definite"}; }
@@ -973,7 +1023,7 @@ int gpb_gpc_laplace(gpb_handle* h, const double* y, const double* khyp, int32_t 
   GPB_CUDA(cudaMemsetAsync(f, 0, static_cast<size_t>(np) * 8 * 8, h->s0));
   GPB_CUDA(cudaMemcpyAsync(yd, y, n * 8, cudaMemcpyHostToDevice, h->s0));
   if (use_f0) GPB_CUDA(cudaMemcpyAsync(f, f_inout, n * 8, cudaMemcpyHostToDevice, h->s0));
-  h->scal.ensure(256);
+  h->scal.ensure(2048);
   double* sc = h->scal.as<double>();
   FactorMat g = m;
   g.rows_total = np + 1;
