@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def run(env_extra, *flags):
     env = dict(os.environ)
     env.update(env_extra)
-    return subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'] + list(flags),
+    return subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0', '--no-ref-calibrate'] + list(flags),
                           capture_output=True, text=True, env=env, timeout=600)
 
 
