@@ -75,12 +75,20 @@ def sweep_nlml(X, y, log_hyp, want_grad=False, group=None, evaluate=None):
     if hi > lo:
         block = vals[:, None] if not want_grad else np.concatenate([vals[:, None], grads], axis=1)
         mine[:hi - lo] = torch.from_numpy(np.ascontiguousarray(block)).to(dev)
-    parts = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(parts, mine, group=group)
+    if backend == 'nccl':
+        # one collective into one buffer and ONE device-to-host copy (a copy per rank costs more than the gather)
+        flat = torch.empty((world, cap, width), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(flat, mine, group=group)
+        host = flat.cpu().numpy()
+        parts = [host[r] for r in range(world)]
+    else:
+        plist = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(plist, mine, group=group)
+        parts = [p.numpy() for p in plist]
     out = np.empty((B, width))
     for r in range(world):
         a, b = shard_bounds(B, world, r)
-        out[a:b] = parts[r][:b - a].cpu().numpy()
+        out[a:b] = parts[r][:b - a]
     return (out[:, 0], out[:, 1:]) if want_grad else out[:, 0]
 
 
