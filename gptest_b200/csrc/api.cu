@@ -40,6 +40,17 @@ double* gpb_handle::pinned(size_t bytes) {
   return h_pinned;
 }
 
+double* gpb_handle::pinned_params(size_t bytes) {
+  if (bytes > h_pinned_par_bytes) {
+    if (h_pinned_par) cudaFreeHost(h_pinned_par);
+    h_pinned_par = nullptr;
+    size_t want = bytes < 4096 ? 4096 : bytes;
+    GPB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_pinned_par), want));
+    h_pinned_par_bytes = want;
+  }
+  return h_pinned_par;
+}
+
 #define GPB_API_BEGIN                                       \
   if (!h) return -1;                                        \
   try {                                                     \
@@ -74,7 +85,9 @@ struct Params {
 Params upload_params(gpb_handle* h, const double* khyp, int64_t batch, int d, bool has_sn2) {
   const int stride = d + (has_sn2 ? 2 : 1);
   const size_t cnt = static_cast<size_t>(batch) * (d + 2);
-  double* host = h->pinned(cnt * 8);
+  // a pinned buffer of its own: the result staging of the same call (pinned()) never overwrites it, and every entry
+  // point synchronises before it returns, so the copy below needs no synchronisation of its own (round 1 blocked here)
+  double* host = h->pinned_params(cnt * 8);
   for (int64_t b = 0; b < batch; ++b) {
     for (int k = 0; k < d; ++k) host[b * d + k] = khyp[b * stride + k];
     host[batch * d + 2 * b] = khyp[b * stride + d];
@@ -82,8 +95,6 @@ Params upload_params(gpb_handle* h, const double* khyp, int64_t batch, int d, bo
   }
   h->params.ensure(cnt * 8);
   GPB_CUDA(cudaMemcpyAsync(h->params.p, host, cnt * 8, cudaMemcpyHostToDevice, h->s0));
-  // the pinned buffer is reused by later calls: make the copy complete before returning to them
-  GPB_CUDA(cudaStreamSynchronize(h->s0));
   return Params{h->params.as<double>(), h->params.as<double>() + batch * d};
 }
 
@@ -227,6 +238,7 @@ int gpb_destroy(gpb_handle* h) {
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   for (auto e : h->tev) if (e) cudaEventDestroy(e);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->h_pinned_par) cudaFreeHost(h->h_pinned_par);
   gpb::grow_release(h);
   if (h->pref_state && h->pref_state_free) h->pref_state_free(h->pref_state);
   delete h;

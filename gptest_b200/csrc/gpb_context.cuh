@@ -105,6 +105,8 @@ struct gpb_handle {
   bool capturing = false;        // a Newton iteration is being captured into a graph: no allocation, no host sync
   double* h_pinned = nullptr;    // pinned staging for small H2D/D2H
   size_t h_pinned_bytes = 0;
+  double* h_pinned_par = nullptr; // second pinned buffer: hyper-parameter uploads (never aliases the result staging above)
+  size_t h_pinned_par_bytes = 0;
 
   std::vector<cudaEvent_t> ev_pool;   // ordering events for the look-ahead
   size_t ev_next = 0;
@@ -127,6 +129,7 @@ struct gpb_handle {
   cudaEvent_t next_event();
   void prepare_capture();        // creates everything a sweep may create lazily (event pool, update streams)
   double* pinned(size_t bytes);
+  double* pinned_params(size_t bytes);
 };
 
 namespace gpb {
