@@ -1,6 +1,7 @@
 // api.cu - the extern "C" boundary (include/gpb200.h): lifecycle, training data, covariance
 // assembly, regression likelihood / prediction, dense factorisation hooks.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/gpb200.h"
@@ -387,18 +388,33 @@ int gpb_gpr_nlml(gpb_handle* h, const double* khyp, double mean, double* nlml, d
   if (grad) return gpb_gpr_nlml_batched(h, khyp, 1, mean, nlml, grad, info);
   Params pr = upload_params(h, khyp, 1, h->d, true);
   const int64_t np = h->n_pad;
-  FactorMat m = alloc_factor(h, 1, 1, 1);
+  // The solve L z = y - m rides on the factorisation.  Round 1 appended y as a row under K: one row of data, but a
+  // whole 128-row tile in every panel TRSM and every update (0.8 % of the work at N = 16384).  Now (fuse_rhs) the
+  // diagonal-tile kernel solves tile k of it and the panel TRSM takes its columns out of the rows below.
+  const bool fuse = h->fuse_rhs != 0 && tile_potrf_fuses_rhs();
+  FactorMat m = fuse ? alloc_factor(h, 1, 0, 0) : alloc_factor(h, 1, 1, 1);
   h->scal.ensure(64);
+  double* zrow = m.A + np * m.ld;
   tic(h, 0);
   prep_train(h, pr, 1);
   build_k_into(h, m, pr, 1, 0);
-  launch_copy_sub_mean(m.A + np * m.ld, h->y.as<double>(), h->n, mean, h->s0);   // y - m  (GPr.py:64-65)
-  ++h->launches;
-  if (np > h->n) GPB_CUDA(cudaMemsetAsync(m.A + np * m.ld + h->n, 0, (np - h->n) * 8, h->s0));
+  if (fuse) {
+    h->aux0.ensure(static_cast<size_t>(np) * 8 * 9);
+    double* rv = h->aux0.as<double>();                                             // 8 partial right-hand sides, then z
+    zrow = rv + 8 * np;
+    GPB_CUDA(cudaMemsetAsync(rv, 0, static_cast<size_t>(np) * 8 * 8, h->s0));
+    launch_copy_sub_mean(rv, h->y.as<double>(), h->n, mean, h->s0);               // partial 0 <- y - m  (GPr.py:64-65)
+    ++h->launches;
+    m.rhs_r = rv; m.rhs_bs = 8 * np; m.rhs_gs = np; m.rhs_z = zrow; m.rhs_zbs = np;
+  } else {
+    launch_copy_sub_mean(zrow, h->y.as<double>(), h->n, mean, h->s0);
+    ++h->launches;
+    if (np > h->n) GPB_CUDA(cudaMemsetAsync(zrow + h->n, 0, (np - h->n) * 8, h->s0));
+  }
   tic(h, 1);
   chol_sweep(h, m, true);
   tic(h, 2);
-  launch_nlml_finish(m.A + np * m.ld, 0, m.diag, 0, np, h->n, h->scal.as<double>(), 1, h->s0);
+  launch_nlml_finish(zrow, 0, m.diag, 0, np, h->n, h->scal.as<double>(), 1, h->s0);
   ++h->launches;
   tic(h, 3);
   double* host = h->pinned(64);

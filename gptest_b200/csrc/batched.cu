@@ -92,17 +92,20 @@ extern "C" int gpb_gpr_nlml_batched(gpb_handle* h, const double* khyp, int64_t B
       a.rows_pad = a.cols_pad = np; a.hyp_dev = hyp2; a.mode = 1; a.clip = 0;
       launch_se_build(a, bc, h->s0);
       // right-hand sides: r = y - mean per problem (scratch), z = L^-1 r
-      h->aux0.ensure(static_cast<size_t>(chunk) * np * 8 * 2);
+      const bool fuse = h->fuse_rhs && tile_potrf_fuses_rhs();
+      h->aux0.ensure(static_cast<size_t>(chunk) * np * 8 * (fuse ? 9 : 2));
       double* rv = h->aux0.as<double>();
-      double* zv = rv + static_cast<size_t>(chunk) * np;
-      launch_set_y_rows(rv, np, 0, h->y.as<double>(), h->n, np, mean, bc, h->s0);
+      double* zv = rv + static_cast<size_t>(chunk) * np * (fuse ? 8 : 1);
       h->launches += 3;
-      if (h->fuse_rhs) {
-        // z = L^-1 r rides on the factorisation: tile k of it is solved right after diagonal tile k, and the panel
-        // TRSM takes its columns out of the rows below while it still holds them (GemmArgs::gemv_*)
-        m.rhs_r = rv; m.rhs_z = zv; m.rhs_bs = np;
+      if (fuse) {
+        // z = L^-1 r rides on the factorisation: tile k of it is solved by the diagonal-tile kernel, and the panel TRSM
+        // takes its columns out of the rows below while it still holds them (8 partial vectors per problem)
+        GPB_CUDA(cudaMemsetAsync(rv, 0, static_cast<size_t>(bc) * np * 8 * 8, h->s0));
+        launch_set_y_rows(rv, 8 * np, 0, h->y.as<double>(), h->n, np, mean, bc, h->s0);      // partial 0 <- y - mean
+        m.rhs_r = rv; m.rhs_bs = 8 * np; m.rhs_gs = np; m.rhs_z = zv; m.rhs_zbs = np;
         chol_sweep(h, m, true);
       } else {
+        launch_set_y_rows(rv, np, 0, h->y.as<double>(), h->n, np, mean, bc, h->s0);
         chol_sweep(h, m, true);
         launch_trsv_l(m.A, m.ld, m.batch_stride, m.Dinv, m.dinv_bs, np, rv, np, zv, np, bc, h->s0);
         h->launches += static_cast<int>(np / TILE);

@@ -155,6 +155,8 @@ struct Sweep {
       a.gemv_z = m.rhs_z + static_cast<int64_t>(k) * TILE;
       a.gemv_r = m.rhs_r;
       a.gemv_bs = m.rhs_bs;
+      a.gemv_gs = m.rhs_gs;
+      a.gemv_zbs = m.rhs_zbs;
     }
     const int n128 = gemm_region_tiles(a);
     if (n128 <= 0) return;
@@ -196,14 +198,12 @@ struct Sweep {
         t.A = m.A; t.lda = m.ld; t.a_batch_stride = m.batch_stride; t.k = k;
         t.Dinv = m.Dinv; t.d_batch_stride = m.dinv_bs;
         t.diag = m.diag; t.diag_batch_stride = m.diag_bs; t.info = m.info; t.pdl = pdl;
+        if (m.rhs_r) {
+          GPB_REQUIRE(tile_potrf_fuses_rhs(), "a right-hand side riding on the factorisation needs potrf_variant 3");
+          t.rhs_r = m.rhs_r; t.rhs_z = m.rhs_z; t.rhs_bs = m.rhs_bs; t.rhs_gs = m.rhs_gs; t.rhs_zbs = m.rhs_zbs;
+        }
         launch_tile_potrf_inv(t, m.batch, st);
         ++h->launches;
-        if (m.rhs_r) {
-          // z_k = W_k r_k: every earlier panel TRSM has already taken its columns out of r_k
-          launch_trsv_l(m.A, m.ld, m.batch_stride, m.Dinv, m.dinv_bs, static_cast<int64_t>(k + 1) * TILE, m.rhs_r, m.rhs_bs, m.rhs_z,
-                        m.rhs_bs, m.batch, st, k);
-          ++h->launches;
-        }
       }
       trsm(k, st);
       update(k + 1, kend, k, k + 1, st);

@@ -66,7 +66,6 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   constexpr int NSPLIT = (BN < BM) ? BM / BN : 1;
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ double gemv_red[GEMV ? 8 : 1][GEMV ? BM : 1];    // per 16-column group: row sums of the fused substitution step
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * STAGE);
   uint64_t* empty = full + GEMM_STAGES;
@@ -242,16 +241,18 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
 
     if (GEMV && p.gemv_r != nullptr) {
-      // r[row] -= X[row][:] . z for the rows of this CTA-tile (BN = 128: the tile spans the whole column block).
-      // The sum over the 128 columns is formed in ONE order whatever the warp layout of the instantiation (which
-      // follows the launch size, i.e. the batch size): per 16-column group the lane's four products in a fixed order,
-      // the four lanes of a row by shuffle, then the eight groups in ascending order through shared memory - a
-      // problem's result does not depend on how many problems share the launch (tests/_sweep_nccl_worker.py).
-      const double* zt = p.gemv_z + static_cast<int64_t>(batch) * p.gemv_bs + wn * BNW;
+      // r_g[row] -= X[row][16 g .. 16 g + 15] . z[16 g ..] for the rows of this CTA-tile (BN = 128: the tile spans the
+      // whole column block).  Per 16-column group the lane's four products in a fixed order, then the four lanes of a
+      // row by shuffle; lane t == 0 owns (group, row).  No reduction across warps: a CTA-wide barrier here made the
+      // factorisation itself irreproducible under the look-ahead schedules (measured, cause not understood), and the
+      // sum must not depend on the warp layout of the instantiation anyway (tests/_sweep_nccl_worker.py).
+      const double* zt = p.gemv_z + static_cast<int64_t>(batch) * p.gemv_zbs + wn * BNW;
+      double* rb = p.gemv_r + static_cast<int64_t>(batch) * p.gemv_bs;
 #pragma unroll
       for (int gn = 0; gn < GN; ++gn) {
         const double z00 = zt[16 * gn + 4 * t], z10 = zt[16 * gn + 4 * t + 1];          // (pn, e) = (0,0), (1,0)
         const double z01 = zt[16 * gn + 4 * t + 2], z11 = zt[16 * gn + 4 * t + 3];      // (0,1), (1,1)
+        double* rg = rb + static_cast<int64_t>(wn * GN + gn) * p.gemv_gs;
 #pragma unroll
         for (int mi = 0; mi < 2 * GM; ++mi) {
           double sdot = acc[mi][gn * 2][0] * z00;
@@ -260,20 +261,10 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           sdot = fma(acc[mi][gn * 2 + 1][1], z11, sdot);
           sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
           sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-          if (t == 0) gemv_red[wn * GN + gn][wm * BMW + 16 * (mi >> 1) + 2 * g + (mi & 1)] = sdot;
+          const int64_t row = static_cast<int64_t>(it) * BM + wm * BMW + 16 * (mi >> 1) + 2 * g + (mi & 1);
+          if (t == 0 && row < p.rows_total) rg[row] -= sdot;
         }
       }
-      __syncthreads();
-      if (threadIdx.x < BM) {
-        const int64_t row = static_cast<int64_t>(it) * BM + threadIdx.x;
-        if (row < p.rows_total) {
-          double tot = gemv_red[0][threadIdx.x];
-#pragma unroll
-          for (int w = 1; w < 8; ++w) tot += gemv_red[w][threadIdx.x];
-          p.gemv_r[static_cast<int64_t>(batch) * p.gemv_bs + row] -= tot;
-        }
-      }
-      __syncthreads();
     }
 
     // ---------------- epilogue: each lane owns 4 consecutive columns per (row, column group) -------

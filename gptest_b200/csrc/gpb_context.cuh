@@ -39,11 +39,12 @@ struct FactorMat {
   double* diag = nullptr;    // per batch n_pad
   int64_t diag_bs = 0;
   int* info = nullptr;       // per batch
-  // optional right-hand side solved along with the factorisation without an appended row (batched fits): r is
-  // overwritten, z <- L^-1 r; per batch entry n_pad doubles each, stride rhs_bs (see GemmArgs::gemv_*)
+  // optional right-hand side solved along with the factorisation without an appended row (GemmArgs::gemv_*):
+  // rhs_r = 8 partial vectors per batch entry (partial g at + g * rhs_gs; the caller puts the right-hand side into
+  // partial 0 and zeros into the others; all are overwritten), z <- L^-1 r
   double* rhs_r = nullptr;
   double* rhs_z = nullptr;
-  int64_t rhs_bs = 0;
+  int64_t rhs_bs = 0, rhs_gs = 0, rhs_zbs = 0;
   TileMaps mapA, mapD;
 };
 

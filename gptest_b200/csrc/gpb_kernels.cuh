@@ -32,12 +32,17 @@ struct GemmArgs {
   int no_stagger;           // chunked schedule: CTAs of several launches share the SMs and dephase by themselves
   int b_tri;                // the B tile is lower triangular (an inverted diagonal tile, the panel TRSM): a warp skips the
                             // k slabs right of its last output column (they multiply zeros)
-  // Forward substitution riding on the panel TRSM (batched fits, batched.cu): with z = the solved tile z_k of the
-  // right-hand side, the CTA that has produced X = rows of L[., tile k] applies  r[row] -= X[row][:] . z  to its rows
-  // (it owns all 128 columns of them), so L is never read again for the solve.  Null: off.
+  // Forward substitution riding on the panel TRSM: with z = the solved tile z_k of the right-hand side, the CTA that
+  // has produced X = rows of L[., tile k] takes  X[row][:] . z  out of the running right-hand side of its rows (it owns
+  // all 128 columns of them), so L is never read again for the solve.  The right-hand side is kept as EIGHT partial
+  // vectors, one per 16-column group of the tile: r[row] = sum_g r_g[row] (summed in order by the reader, the
+  // diagonal-tile kernel).  Group g of a row is owned by exactly one lane of one CTA of the launch, so there is no
+  // reduction across warps and no barrier in the epilogue, and the order of every sum is fixed.  Null: off.
   const double* gemv_z;     // per batch entry: 128 doubles (z_k)
-  double* gemv_r;           // per batch entry: the running right-hand side, indexed by global row
-  int64_t gemv_bs;          // elements between batch entries of z / r
+  double* gemv_r;           // per batch entry: 8 partial right-hand sides, group g at + g * gemv_gs, indexed by global row
+  int64_t gemv_bs;          // elements between batch entries of r
+  int64_t gemv_gs;          // elements between the partial vectors of one batch entry
+  int64_t gemv_zbs;         // elements between batch entries of z
   int sym_lower;            // symmetric update of a factorisation: only the lower triangle of C is ever read, so warp
                             // tiles that lie strictly above the diagonal are neither computed nor stored
 };
@@ -71,12 +76,18 @@ struct TilePotrfArgs {
   int64_t diag_batch_stride;
   int* info;                // per batch: first failing pivot (1-based global index), 0 = ok
   int pdl;                  // launch with programmatic stream serialisation
+  // optional right-hand side riding on the factorisation (GemmArgs::gemv_*): the kernel also solves tile k of it,
+  // z_k = W_k r_k, once W is complete (variant 3 only; see tile_potrf_fuses_rhs)
+  const double* rhs_r;      // 8 partial vectors per batch entry (see GemmArgs::gemv_r)
+  double* rhs_z;
+  int64_t rhs_bs, rhs_gs, rhs_zbs;
   long long* dbg;           // optional (tools/micro/tp3_bench.cu): clock64() of the phase boundaries, per warp; normally null
 };
 void launch_tile_potrf_inv(TilePotrfArgs a, int batch, cudaStream_t st);
 void tile_potrf_init();
 void tile_potrf_set_variant(int v);          // 3 (default): blocked in-CTA kernel (tile_potrf3.cu)  2: register-resident sweep
-void tile_potrf_set_refine(int on);          // variant 3: corrected (default) or bare rsqrt pivots
+void tile_potrf_set_refine(int on);
+bool tile_potrf_fuses_rhs();                 // the selected variant computes z_k = W_k r_k itself (TilePotrfArgs::rhs_*)          // variant 3: corrected (default) or bare rsqrt pivots
 
 // ---------------------------------------------------------------------------------------
 // SE-ARD covariance assembly

@@ -191,6 +191,7 @@ static int g_potrf_variant = 3;
 static int g_potrf_refine = 1;        // variant 3: one correction step on rsqrt for 1/d and d (<= 1 ulp) or the bare rsqrt
 void tile_potrf_set_variant(int v) { g_potrf_variant = (v == 2) ? 2 : 3; }
 void tile_potrf_set_refine(int on) { g_potrf_refine = on != 0; }
+bool tile_potrf_fuses_rhs() { return g_potrf_variant != 2; }
 
 void tile_potrf_init() {
   GPB_CUDA(cudaFuncSetAttribute(tile_potrf_inv_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM));
