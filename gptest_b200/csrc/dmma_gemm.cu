@@ -243,9 +243,10 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     if (GEMV && p.gemv_r != nullptr) {
       // r_g[row] -= X[row][16 g .. 16 g + 15] . z[16 g ..] for the rows of this CTA-tile (BN = 128: the tile spans the
       // whole column block).  Per 16-column group the lane's four products in a fixed order, then the four lanes of a
-      // row by shuffle; lane t == 0 owns (group, row).  No reduction across warps: a CTA-wide barrier here made the
-      // factorisation itself irreproducible under the look-ahead schedules (measured, cause not understood), and the
-      // sum must not depend on the warp layout of the instantiation anyway (tests/_sweep_nccl_worker.py).
+      // row by shuffle; lane t == 0 owns (group, row).  No reduction across warps: the sum must not depend on the warp
+      // layout of the instantiation (tests/_sweep_nccl_worker.py), and a first version that reduced the groups through
+      // shared memory behind CTA barriers gave irreproducible results under the look-ahead schedules at N >= 9216
+      // (cause not found; this form is checked by tools/fused_rhs_determinism.py and tests/test_gpu_config_sizes.py).
       const double* zt = p.gemv_z + static_cast<int64_t>(batch) * p.gemv_zbs + wn * BNW;
       double* rb = p.gemv_r + static_cast<int64_t>(batch) * p.gemv_bs;
 #pragma unroll

@@ -45,6 +45,24 @@ def test_c2_fit_and_predict_match_oracle_at_n16384(handle):
     assert np.isfinite(g2).all() and g2.shape == (10,)
 
 
+def test_fit_is_reproducible_under_the_lookahead_schedule_with_and_without_the_fused_solve(handle):
+    """N = 9216 is past the switch to the look-ahead / multi-stream schedule (nb_switch2): repeated fits return the
+    same bits, and the forward substitution riding on the factorisation (fuse_rhs) agrees with the
+    appended-row solve of round 1."""
+    X, y, _, lh = cfg.make_c2(n=9216)
+    kh = cfg.khyp_of(lh)
+    handle.set_train(X, y)
+    try:
+        handle.set_option('fuse_rhs', 0)
+        plain = [handle.gpr_nlml(kh) for _ in range(3)]
+        handle.set_option('fuse_rhs', 1)
+        fused = [handle.gpr_nlml(kh) for _ in range(8)]
+    finally:
+        handle.set_option('fuse_rhs', 1)
+    assert len(set(plain)) == 1 and len(set(fused)) == 1, (plain, fused)
+    assert abs(fused[0] - plain[0]) <= 1e-12 * abs(plain[0])
+
+
 def test_c3_gpc_matches_oracle_at_n4096_and_n8192(handle):
     """R&W Alg. 3.1 (GPc.py intent; parity unpinned): full convergence at N=4096, the first two Newton steps at
     the C3 size N=8192 (trace and mode after the same count)."""
