@@ -256,6 +256,8 @@ int gpb_set_option(gpb_handle* h, const char* name, int64_t value) {
   else if (!strcmp(name, "batch_plain_width")) h->batch_plain_width = static_cast<int>(value < 1 ? 1 : (value > 8 ? 8 : value));
   else if (!strcmp(name, "small_tile_threshold")) h->small_tile_threshold = value;
   else if (!strcmp(name, "thin_tile_max")) h->thin_tile_max = value;
+  else if (!strcmp(name, "trsm_tile_threshold")) h->trsm_tile_threshold = value;
+  else if (!strcmp(name, "batch_small_k")) h->batch_small_k = static_cast<int>(value);
   else if (!strcmp(name, "tri_skip")) h->tri_skip = value != 0;
   else if (!strcmp(name, "fuse_rhs")) h->fuse_rhs = value != 0;
   else if (!strcmp(name, "split_tiles")) h->split_tiles = value != 0;
@@ -263,6 +265,7 @@ int gpb_set_option(gpb_handle* h, const char* name, int64_t value) {
   else if (!strcmp(name, "stagger")) dmma_gemm_set_stagger(static_cast<int>(value));
   else if (!strcmp(name, "pdl")) dmma_gemm_set_pdl(static_cast<int>(value));
   else if (!strcmp(name, "fine_warps")) dmma_gemm_set_fine_warps(static_cast<int>(value));
+  else if (!strcmp(name, "trsm_balance")) dmma_gemm_set_trsm_balance(static_cast<int>(value));
   else if (!strcmp(name, "potrf_variant")) tile_potrf_set_variant(static_cast<int>(value));
   else if (!strcmp(name, "potrf_refine")) tile_potrf_set_refine(static_cast<int>(value));
   else if (!strcmp(name, "dag_streams")) h->dag_streams = static_cast<int>(value < 0 ? 0 : (value > 16 ? 16 : value));

@@ -131,7 +131,11 @@ struct Sweep {
       ++h->launches;
       return;
     }
-    if (!big_tiles && static_cast<int64_t>(n128) * m.batch < h->small_tile_threshold) {
+    // batches of matrices with short k (the plain-order sweeps, K <= 512): 64 x 64 CTA-tiles, three per SM, whatever the
+    // tile count - finer skipping of the unused half of diagonal tiles and more CTAs to cover the fill and drain of
+    // an 8..32-slab k loop (1024 x N=2048: 107.2 -> 103.4 ms, 128 problems 13.81 -> 13.40 ms)
+    const bool short_k_batch = m.batch > 1 && !a.k_from_row && a.nk * GEMM_KB <= h->batch_small_k;
+    if (!big_tiles && (static_cast<int64_t>(n128) * m.batch < h->small_tile_threshold || short_k_batch)) {
       launch_dmma_gemm(ma.m64, mb.m64, gemm_args_to_64(a), m.batch, st, 64);
     } else if (h->split_tiles) {
       launch_dmma_gemm(ma.m128, mb.m64, a, m.batch, st, 12864);
@@ -170,7 +174,7 @@ struct Sweep {
       ++h->launches;
       return;
     }
-    if (static_cast<int64_t>(n128) * m.batch < h->small_tile_threshold) {
+    if (static_cast<int64_t>(n128) * m.batch < h->trsm_tile_threshold) {
       GemmArgs b = a;
       b.i0 = 2 * a.i0;
       const int r64 = (a.rows_total + 63) / 64;

@@ -325,6 +325,8 @@ static int g_fine_warps = 1;
 void dmma_gemm_set_fine_warps(int on) { g_fine_warps = on != 0; }
 static int g_stagger = 1;
 void dmma_gemm_set_stagger(int on) { g_stagger = on != 0; }
+static int g_trsm_balance = 1;
+void dmma_gemm_set_trsm_balance(int mode) { g_trsm_balance = mode; }
 
 void dmma_gemm_init() {
   GPB_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel<128, 128, 2, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -425,7 +427,11 @@ void launch_dmma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmArgs
                    mapA, mapB, a);
   } else {
     // 64 x 128: rows in units of 64, columns in units of 128 (mapA with 64-row boxes, mapB with 128-row boxes)
-    const bool fine = g_fine_warps && static_cast<int64_t>(ntiles) * a.nbatch <= g_num_sms;
+    // triangular B (panel TRSM): the light and the heavy column groups have to be spread over the four schedulers.
+    // 8 warps (2 x 4, second row mirrored) do that inside one CTA; with 4 warps (2 x 2) a scheduler holds one warp of
+    // each resident CTA and both are of the same kind.  128-problem slice of the sweep: 14.32 -> 13.76 ms, same bits
+    // (tools/sweep_balance.py; mirroring the assignment in every other 4-warp CTA instead: no gain).
+    const bool fine = (g_fine_warps && static_cast<int64_t>(ntiles) * a.nbatch <= g_num_sms) || (a.b_tri && g_trsm_balance);
     if (fine && gemv)
       launch_chain(dmma_gemm_nt_kernel<64, 128, 2, 4, 2, true>, grid_for(ntiles, 2), dim3(8 * 32), smem_bytes(64, 128), st, pdl,
                    mapA, mapB, a);

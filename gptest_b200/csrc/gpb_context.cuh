@@ -89,6 +89,9 @@ struct gpb_handle {
   int tri_skip = 1;              // skip the zero half of the inverted diagonal tile in the panel TRSM and the warp tiles above
                                  // the diagonal in the symmetric updates (same results, fewer DMMAs)
   int64_t thin_tile_max = 74;    // panel TRSM / single-column update launches with at most this many 128-tiles use 32-row CTA-tiles
+  int64_t trsm_tile_threshold = 1LL << 40;   // the panel TRSM's switch from 64 x 128 (two CTAs of 8 warps per SM) to 128 x 128 CTA-tiles (one):
+                                             // never by default - 1024 x N=2048 sweep 109.3 -> 107.2 ms, single fits unchanged (tools/sweep_trsm_tiles.py)
+  int batch_small_k = 512;              // batched updates with k up to this use 64 x 64 CTA-tiles regardless of the tile count
   int64_t small_tile_threshold = 2400;  // launches with fewer 128-tiles than this use 64-tiles (tuned: r01_tune_potrf.json)
 
   // training data (GPr.py:25-26 keeps trainInput / trainTarget on the object)
