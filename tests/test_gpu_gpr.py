@@ -366,6 +366,38 @@ def test_full_size_fit_properties(handle):
     assert np.abs(cov - vref).max() < 1e-9
 
 
+def test_fit_with_more_than_2_to_31_matrix_elements(handle):
+    """Maximum sizes: N = 47104 (368 tiles) puts 2.2e9 elements = 17.7 GB into the factor, past every 32-bit element and
+    byte offset.  Checked against cuSOLVER through torch (checker only) on the matrix our own kernel assembles."""
+    import torch
+    rng = np.random.default_rng(3)
+    n, d = 47104, 8
+    X = rng.random((n, d))
+    w = rng.standard_normal(d)
+    y = np.sin(X @ w) + 0.1 * rng.standard_normal(n)
+    lh = np.log([0.5] * d + [1.0, 0.1])
+    kh = khyp_of(lh)
+    handle.set_train(X, y)
+    v = handle.gpr_nlml(kh)
+    v2 = handle.gpr_nlml(kh)
+    assert v == v2                                            # run-to-run identical at this size too
+    K = torch.empty((n, n), dtype=torch.float64, device='cuda')
+    handle.kxx_dev(kh, K.data_ptr())
+    torch.cuda.synchronize()
+    tail = K[-200:, -200:].cpu().numpy()                      # the far corner of the matrix: offsets past 2^31 elements
+    assert np.abs(tail - gpr_oracle.kxx(lh, X[-200:])).max() < 2e-14
+    Lt = torch.linalg.cholesky(K)
+    del K
+    yt = torch.from_numpy(y).cuda()
+    zt = torch.linalg.solve_triangular(Lt, yt[:, None], upper=False)[:, 0]
+    ref = (0.5 * (zt @ zt) + torch.log(torch.diagonal(Lt)).sum()).item() + 0.5 * n * np.log(2 * np.pi)
+    del Lt
+    torch.cuda.empty_cache()
+    assert abs(v - ref) <= 1e-8 * abs(ref), (v, ref)
+    handle.set_train(X[:256], y[:256])                        # leave a small work space behind
+    handle.gpr_nlml(kh)
+
+
 # ---------------------------------------------------------------------------------------
 # gradients (not in the reference: textbook formula, pinned by finite differences in test_oracle)
 # ---------------------------------------------------------------------------------------
