@@ -260,6 +260,7 @@ int gpb_set_option(gpb_handle* h, const char* name, int64_t value) {
   else if (!strcmp(name, "batch_small_k")) h->batch_small_k = static_cast<int>(value);
   else if (!strcmp(name, "tri_skip")) h->tri_skip = value != 0;
   else if (!strcmp(name, "fuse_rhs")) h->fuse_rhs = value != 0;
+  else if (!strcmp(name, "fuse_min_tiles")) h->fuse_min_tiles = static_cast<int>(value);
   else if (!strcmp(name, "split_tiles")) h->split_tiles = value != 0;
   else if (!strcmp(name, "persistent_waves")) dmma_gemm_set_persistent(static_cast<int>(value));
   else if (!strcmp(name, "stagger")) dmma_gemm_set_stagger(static_cast<int>(value));
@@ -394,7 +395,11 @@ int gpb_gpr_nlml(gpb_handle* h, const double* khyp, double mean, double* nlml, d
   // The solve L z = y - m rides on the factorisation.  Round 1 appended y as a row under K: one row of data, but a
   // whole 128-row tile in every panel TRSM and every update (0.8 % of the work at N = 16384).  Now (fuse_rhs) the
   // diagonal-tile kernel solves tile k of it and the panel TRSM takes its columns out of the rows below.
-  const bool fuse = h->fuse_rhs != 0 && tile_potrf_fuses_rhs();
+  // ... from fuse_min_tiles tile columns on: the z_k step and the epilogue of the panel TRSM lengthen the chain of panel
+  // kernels by ~2.5 us per tile column, an appended row does not (its tiles run beside the others), so below N ~ 9000,
+  // where the chain is a visible part of the run time, the row wins (N = 2048: 0.703 vs 0.753 ms, 4096: 1.79 vs 1.83,
+  // 8192: 7.56 vs 7.57, 16384: 47.2 vs 46.6)
+  const bool fuse = h->fuse_rhs != 0 && tile_potrf_fuses_rhs() && np / TILE >= h->fuse_min_tiles;
   FactorMat m = fuse ? alloc_factor(h, 1, 0, 0) : alloc_factor(h, 1, 1, 1);
   h->scal.ensure(64);
   double* zrow = m.A + np * m.ld;

@@ -85,6 +85,7 @@ struct gpb_handle {
                                  // (measured: N=16384 B=4 47.5 vs 50.2 ms/fit, N=4096 B=8 1.08 vs 1.20; 1024x2048 neutral)
   int split_tiles = 1;           // big launches: 1 = 128x64 CTAs, two per SM (finer grain: the look-ahead panel
                                  // kernels get SMs sooner, N=16384: 49.7 vs 52.4 ms); 0 = 128x128, one per SM
+  int fuse_min_tiles = 72;       // single fits: the solve rides on the factorisation from this many tile columns on (api.cu)
   int fuse_rhs = 1;              // batched fits: forward substitution fused into the panel TRSM (no second pass over L)
   int tri_skip = 1;              // skip the zero half of the inverted diagonal tile in the panel TRSM and the warp tiles above
                                  // the diagonal in the symmetric updates (same results, fewer DMMAs)

@@ -46,9 +46,9 @@ def test_c2_fit_and_predict_match_oracle_at_n16384(handle):
 
 
 def test_fit_is_reproducible_under_the_lookahead_schedule_with_and_without_the_fused_solve(handle):
-    """N = 9216 is past the switch to the look-ahead / multi-stream schedule (nb_switch2): repeated fits return the
-    same bits, and the forward substitution riding on the factorisation (fuse_rhs) agrees with the
-    appended-row solve of round 1."""
+    """N = 9216 is past the switch to the look-ahead / multi-stream schedule (nb_switch2) and at the size from which
+    single fits let the forward substitution ride on the factorisation (fuse_min_tiles = 72 tile columns):
+    repeated fits return the same bits, and the result agrees with the appended-row solve of round 1."""
     X, y, _, lh = cfg.make_c2(n=9216)
     kh = cfg.khyp_of(lh)
     handle.set_train(X, y)

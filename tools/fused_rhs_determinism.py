@@ -4,6 +4,7 @@ import numpy as np
 import bench_configs as cfg
 from gptest_b200 import _lib
 h = _lib.Handle(0)
+h.set_option('fuse_min_tiles', 0)      # force the fused solve at every size
 for n in (4096, 9216, 12288, 16384):
     X, y, Z, lh = cfg.make_c2(n=n)
     kh = cfg.khyp_of(lh)
