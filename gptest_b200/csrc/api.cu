@@ -267,6 +267,7 @@ int gpb_set_option(gpb_handle* h, const char* name, int64_t value) {
   else if (!strcmp(name, "pdl")) dmma_gemm_set_pdl(static_cast<int>(value));
   else if (!strcmp(name, "fine_warps")) dmma_gemm_set_fine_warps(static_cast<int>(value));
   else if (!strcmp(name, "trsm_balance")) dmma_gemm_set_trsm_balance(static_cast<int>(value));
+  else if (!strcmp(name, "trsm_persist")) dmma_gemm_set_trsm_persist(static_cast<int>(value));
   else if (!strcmp(name, "potrf_variant")) tile_potrf_set_variant(static_cast<int>(value));
   else if (!strcmp(name, "potrf_refine")) tile_potrf_set_refine(static_cast<int>(value));
   else if (!strcmp(name, "dag_streams")) h->dag_streams = static_cast<int>(value < 0 ? 0 : (value > 16 ? 16 : value));

@@ -60,6 +60,7 @@ void dmma_gemm_init();                           // sets the dynamic smem attrib
 void dmma_gemm_set_persistent(int waves);        // 0 (default): one CTA per tile; n: persistent grid of n waves
 void dmma_gemm_set_pdl(int mode);               // programmatic dependent launch: 0 off, 1 small launches (default), 2 all
 void dmma_gemm_set_trsm_balance(int mode);     // 64 x 128 panel TRSM with a triangular B: 1 (default) 8-warp CTAs, 0 by launch size as elsewhere
+void dmma_gemm_set_trsm_persist(int waves);    // > 0: the panel TRSM runs as that many resident waves of CTAs walking the tile list
 void dmma_gemm_set_fine_warps(int on);          // 1 (default): 8-warp CTAs for launches of at most one CTA per SM
 void dmma_gemm_set_stagger(int on);              // 1 (default): phase-shift co-resident CTAs of the 2-per-SM variants
 

@@ -54,10 +54,10 @@ const char* gpb_last_error(gpb_handle* h);            /* h may be NULL: last cre
  * the default; 2: the register-resident sweep of round 1), "potrf_refine", "thin_tile_max" (32-row CTA-tiles on the panel
  * chain), "tri_skip" (zero / unused halves skipped in the panel TRSM and the symmetric updates), "fuse_rhs" (the forward
  * substitution L z = y - m rides on the factorisation: diagonal-tile kernel + panel TRSM epilogue; 0 = appended row /
- * separate pass as in round 1), "trsm_balance" (8-warp CTAs for a panel TRSM with a triangular B), "trsm_tile_threshold"
+ * separate pass as in round 1), "trsm_balance" (8-warp CTAs for a panel TRSM with a triangular B), "trsm_persist" (resident waves of its grid), "trsm_tile_threshold"
  * (128-tile count from which the panel TRSM uses 128 x 128 CTA-tiles; default never), "batch_small_k" (batched updates
  * with k up to this use 64 x 64 CTA-tiles), "batch_plain_width", "fine_warps", "persistent_waves", "stagger" (see
- * gpb_context.cuh).  "pdl", "potrf_variant", "potrf_refine", "fine_warps", "trsm_balance", "persistent_waves" and
+ * gpb_context.cuh).  "pdl", "potrf_variant", "potrf_refine", "fine_warps", "trsm_balance", "trsm_persist", "persistent_waves" and
  * "stagger" are process-wide, the rest per handle.  Returns <0 if unknown. */
 int gpb_set_option(gpb_handle* h, const char* name, int64_t value);
 /* stage times (ms) of the last GPr/potrf call measured with CUDA events on the handle's
