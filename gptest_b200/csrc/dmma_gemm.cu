@@ -23,8 +23,14 @@
 //   * instantiations: 128x64 (4 warps of 64x32, two CTAs per SM, second one phase-shifted) for the big
 //     trailing updates - per 16-wide slab a warp issues 128 DMMA for 48 LDS.64, the FP64 tensor pipe
 //     is the only busy unit (92 % active at K=512); 128x128 (8 warps, 1 CTA/SM); 64x64 (4 warps of
-//     32x32, 3 CTAs/SM) for launches on the panel's critical path or too small to fill 148 SMs;
-//     64x128 for the in-place panel TRSM (a CTA must own all 128 output columns of its rows).
+//     32x32, 3 CTAs/SM) for launches on the panel's critical path or too small to fill 148 SMs, and for every
+//     short-k update of a batch of small matrices; 64x128 (8 warps, 2 CTAs/SM) for the in-place panel TRSM (a CTA
+//     must own all 128 output columns of its rows); 32x128 and 32x64 (8 warps) for the TRSM and the next-column
+//     update of a small matrix, where the launch is one wave and its duration is the latency of ONE CTA.
+//   * round 2: a triangular B operand (the inverted diagonal tile) lets a warp stop after the k slabs its columns
+//     need (b_tri), symmetric updates skip warp tiles above the diagonal (sym_lower), and the panel-TRSM shapes have
+//     a second instantiation (GEMV) whose epilogue takes the just-computed columns out of the running right-hand side
+//     of the forward substitution.
 #include "gpb_kernels.cuh"
 
 namespace gpb {
