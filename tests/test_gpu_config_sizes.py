@@ -43,6 +43,15 @@ def test_c2_fit_and_predict_match_oracle_at_n16384(handle):
     v2, g2 = handle.gpr_nlml(kh, want_grad=True)
     assert abs(v2 - ref_nlml) <= 1e-8 * abs(ref_nlml)
     assert np.isfinite(g2).all() and g2.shape == (10,)
+    # the gradient (d nlml / d log-hyper-parameters, oracle-checked at small N in test_gpu_gpr.py) against central
+    # differences of the full-size value along two directions: a size-independent property, two extra fits each
+    rng = np.random.default_rng(1)
+    for _ in range(2):
+        u = rng.standard_normal(lh.size)
+        u /= np.linalg.norm(u)
+        eps = 1e-5
+        fd = (handle.gpr_nlml(cfg.khyp_of(lh + eps * u)) - handle.gpr_nlml(cfg.khyp_of(lh - eps * u))) / (2 * eps)
+        assert abs(fd - g2 @ u) <= 1e-5 * np.linalg.norm(g2), (fd, g2 @ u)
 
 
 def test_fit_is_reproducible_under_the_lookahead_schedule_with_and_without_the_fused_solve(handle):
